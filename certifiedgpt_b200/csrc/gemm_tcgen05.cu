@@ -1,0 +1,370 @@
+// Dense bf16 GEMM core for sm_100a:  out[M,N] = epilogue(A[M,K] . W[N,K]^T)
+//
+// Every nn.Linear / Conv2d-as-GEMM on the smoothing hot path goes through this kernel
+// (SURVEY.md 2.3 rows K2,K3,K5,K6,K7,K9-K12,K14,K15; reference call sites
+// eva_vit.py:126-131,151,60-64,202; Qformer.py:128-135,285-289,358-375; minigpt4.py:141;
+// HF LlamaForCausalLM linears).  Both operands are K-major, which is the native
+// nn.Linear weight layout ([out,in]), so no transposes exist anywhere.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled A/B k-blocks -> smem ring
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma (UMMA 128 x BN x 16), fp32
+//                                accumulators in TMEM, two accumulator stages
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue       : tcgen05.ld -> bias / GELU / SwiGLU / residual / pos-embed
+//                                -> bf16 or fp32 global stores, overlapped with the next
+//                                tile's MMAs through the second TMEM stage
+#include "common.cuh"
+#include "ops.h"
+
+namespace cgpt {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 176 ? 5 : 6);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
+  static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
+};
+
+struct EpiParams {
+  void* out;
+  long long ldo;
+  int out_f32;
+  const float* bias;
+  const void* resid;
+  long long ldr;
+  int resid_f32;
+  int act;
+  const float* row_add;
+  long long ld_row_add;
+  int row_period;     // >0: m -> (m / period, m % period)
+  int row_add_offset; // row_add row = (m % period) + offset
+  int remap_stride;   // out row = (m / period) * remap_stride + remap_offset + (m % period)
+  int remap_offset;
+};
+
+// process `NC` consecutive accumulator columns of one row and store them
+template <int NC>
+__device__ __forceinline__ void epilogue_store(const uint32_t* acc, const EpiParams& p, int m,
+                                               long long out_row, int n0, int N) {
+  float v[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NC; i += 4) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+  }
+  if (p.act == CGPT_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (p.act == CGPT_ACT_SWIGLU) {
+    // weight rows are interleaved (gate_j, up_j): out[:, j] = silu(gate_j) * up_j
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + (n0 >> 1);
+    uint32_t w[NC / 4];
+#pragma unroll
+    for (int i = 0; i < NC / 4; ++i)
+      w[i] = pack_bf16x2(silu(v[4 * i]) * v[4 * i + 1], silu(v[4 * i + 2]) * v[4 * i + 3]);
+#pragma unroll
+    for (int i = 0; i < NC / 16; ++i)
+      *reinterpret_cast<uint4*>(o + 8 * i) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    return;
+  }
+  if (p.row_add != nullptr) {
+    const float* ra = p.row_add + (long long)((m % p.row_period) + p.row_add_offset) * p.ld_row_add + n0;
+#pragma unroll
+    for (int i = 0; i < NC; i += 4) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(ra + i));
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+  }
+  if (p.resid != nullptr) {
+    if (p.resid_f32) {
+      const float* r = reinterpret_cast<const float*>(p.resid) + out_row * p.ldr + n0;
+#pragma unroll
+      for (int i = 0; i < NC; i += 4) {
+        float4 b = *reinterpret_cast<const float4*>(r + i);
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    } else {
+      const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.resid) + out_row * p.ldr + n0;
+#pragma unroll
+      for (int i = 0; i < NC; i += 8) {
+        uint4 b = *reinterpret_cast<const uint4*>(r + i);
+        v[i] += bf16_lo(b.x); v[i + 1] += bf16_hi(b.x);
+        v[i + 2] += bf16_lo(b.y); v[i + 3] += bf16_hi(b.y);
+        v[i + 4] += bf16_lo(b.z); v[i + 5] += bf16_hi(b.z);
+        v[i + 6] += bf16_lo(b.w); v[i + 7] += bf16_hi(b.w);
+      }
+    }
+  }
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
+#pragma unroll
+    for (int i = 0; i < NC; i += 4)
+      *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n0;
+#pragma unroll
+    for (int i = 0; i < NC; i += 8)
+      *reinterpret_cast<uint4*>(o + i) =
+          make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                     pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
+                         const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
+                         EpiParams epi) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                  // [STAGES] TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * STAGES;    // [2] MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in (addr >> 4) units
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int m = m_blk * BM + quarter * 32 + lane;
+      const bool row_ok = m < M;
+      long long out_row = m;
+      if (epi.row_period > 0 && epi.remap_stride > 0)
+        out_row = (long long)(m / epi.row_period) * epi.remap_stride + epi.remap_offset +
+                  (m % epi.row_period);
+      const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld_x16(t_row + c * 16, r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 16;
+        if (row_ok && n0 < N) epilogue_store<16>(r, epi, m, out_row, n0, N);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// K-major bf16 matrix [rows, K] with leading dimension ld (elements); box = 64 x box_rows, SW128
+static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long K, long long ld,
+                     int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  CGPT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CGPT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rows=%lld K=%lld ld=%lld ptr=%p",
+               (int)r, rows, K, ld, ptr);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int g_gemm_launches = 0;
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+                       const EpiParams& epi, int max_ctas, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    CGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  ++g_gemm_launches;
+  return 0;
+}
+
+int gemm_launch_count() { return g_gemm_launches; }
+
+// pick the N tile: exact divisors first (no wasted MMA columns), else 256 with masking
+static int pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 176 == 0) return 176;
+  if (N % 128 == 0) return 128;
+  return N >= 256 ? 256 : (N > 128 ? 176 : 128);
+}
+
+int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+              const cgpt_gemm_epilogue* e, int force_bn, cudaStream_t stream) {
+  CGPT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  CGPT_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
+               "gemm: K, lda, ldw must be multiples of 8 (16-byte TMA rows): K=%d lda=%lld ldw=%lld",
+               K, lda, ldw);
+  CGPT_REQUIRE(N % 16 == 0, "gemm: N must be a multiple of 16 (got %d)", N);
+  CGPT_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+               "gemm: A and W must be 16-byte aligned");
+  CGPT_REQUIRE(e != nullptr && e->out != nullptr, "gemm: epilogue/out is null");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    CGPT_CHECK_CUDA(cudaGetDevice(&dev));
+    CGPT_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  EpiParams p;
+  p.out = e->out; p.ldo = e->ldo; p.out_f32 = e->out_dtype == CGPT_DT_F32;
+  p.bias = e->bias;
+  p.resid = e->resid; p.ldr = e->ldr; p.resid_f32 = e->resid_dtype == CGPT_DT_F32;
+  p.act = e->act;
+  p.row_add = e->row_add; p.ld_row_add = e->ld_row_add;
+  p.row_period = e->row_period; p.row_add_offset = e->row_add_offset;
+  p.remap_stride = e->remap_stride; p.remap_offset = e->remap_offset;
+  CGPT_REQUIRE(p.row_add == nullptr || p.row_period > 0, "gemm: row_add needs row_period > 0");
+  CGPT_REQUIRE(p.act != CGPT_ACT_SWIGLU || (!p.out_f32 && p.resid == nullptr && p.row_add == nullptr),
+               "gemm: SwiGLU epilogue writes bf16 and takes no residual");
+
+  const int bn = force_bn > 0 ? force_bn : pick_bn(N);
+  CUtensorMap ta, tb;
+  if (int rc = make_tmap(&ta, A, M, K, lda, BM)) return rc;
+  if (int rc = make_tmap(&tb, W, N, K, ldw, bn)) return rc;
+  switch (bn) {
+    case 256: return launch_gemm<256>(ta, tb, M, N, K, p, e->max_ctas, stream);
+    case 176: return launch_gemm<176>(ta, tb, M, N, K, p, e->max_ctas, stream);
+    case 128: return launch_gemm<128>(ta, tb, M, N, K, p, e->max_ctas, stream);
+    default: CGPT_REQUIRE(false, "gemm: unsupported N tile %d", bn);
+  }
+  return 0;
+}
+
+}  // namespace cgpt

@@ -1,0 +1,73 @@
+/* certifiedgpt_b200 C-ABI  (libcgpt.so, sm_100a only)
+ *
+ * Drop-in boundary for the Monte-Carlo randomized-smoothing hot path of
+ * leodesouza/certifiedGPT.  The reference has no FFI (it is pure Python on torch /
+ * torch_xla); these entry points are what a Python binding for that path loads with
+ * ctypes.  Each declaration cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = error; cgpt_last_error() gives the
+ *     thread-local message.  No C++ exception crosses this boundary.
+ *   - all device buffers are caller-owned (e.g. torch tensors' data_ptr()); the library
+ *     allocates nothing on the device.  Scratch is passed in explicitly.
+ *   - every launch is asynchronous on the cudaStream_t passed as `void* stream`.
+ *   - one host thread per GPU / rank; handles are not shared across threads.
+ *   - bf16 = __nv_bfloat16 bit pattern; "f32 vectors" (biases, LayerNorm/RMSNorm
+ *     parameters, position embeddings) are float.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef CGPT_H_
+#define CGPT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGPT_ABI_VERSION 1
+
+enum { CGPT_DT_BF16 = 0, CGPT_DT_F32 = 1 };
+enum { CGPT_ACT_NONE = 0, CGPT_ACT_GELU = 1, CGPT_ACT_SWIGLU = 2 };
+enum { CGPT_NOISE_GAUSSIAN = 0, CGPT_NOISE_UNIFORM = 1 };
+/* where the noise is added relative to the BLIP Normalize step
+ * (processors/base_processor.py:17-34):
+ *   NORMALIZED: x is already normalised, out = x + sigma*eps   (smoothing.py:95-97 as written)
+ *   PIXEL     : x is in [0,1] pixel space, out = (x + sigma*eps - mean)/std  (north_star) */
+enum { CGPT_SPACE_NORMALIZED = 0, CGPT_SPACE_PIXEL = 1 };
+
+const char* cgpt_last_error(void);
+int cgpt_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+long long cgpt_launch_count(void);
+
+/* ---------------------------------------------------------------- dense GEMM core
+ * out[M,N] = epilogue(A[M,K] . W[N,K]^T), bf16 inputs, fp32 accumulate (tcgen05 + TMEM + TMA).
+ * Replaces every nn.Linear / patch Conv2d on the path: eva_vit.py:202 (PatchEmbed.proj),
+ * :126-131 (qkv), :151 (proj), :60-64 (fc1/fc2); Qformer.py:128-135,285-289,358-375;
+ * minigpt4.py:76-78,141 (llama_proj); HF LlamaForCausalLM q/k/v/o/gate/up/down/lm_head. */
+typedef struct cgpt_gemm_epilogue {
+  void* out;            /* [rows, ldo] bf16 or f32                                          */
+  int64_t ldo;          /* elements                                                         */
+  int out_dtype;        /* CGPT_DT_*                                                        */
+  const float* bias;    /* [N] or NULL                                                      */
+  const void* resid;    /* residual added after activation, indexed like `out`, or NULL     */
+  int64_t ldr;
+  int resid_dtype;
+  int act;              /* CGPT_ACT_*; SWIGLU: W rows interleaved (gate_j, up_j), out has N/2 cols */
+  const float* row_add; /* e.g. pos_embed: adds row_add[(m % row_period) + row_add_offset, n] */
+  int64_t ld_row_add;
+  int row_period;
+  int row_add_offset;
+  int remap_stride;     /* >0: out row = (m / row_period) * remap_stride + remap_offset + m % row_period */
+  int remap_offset;
+  int max_ctas;         /* 0 = one persistent CTA per SM                                    */
+} cgpt_gemm_epilogue;
+
+int cgpt_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                   const cgpt_gemm_epilogue* epi, int force_bn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGPT_H_ */
