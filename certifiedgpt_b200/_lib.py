@@ -53,6 +53,8 @@ def load(build_if_missing=False):
     lib.cgpt_last_error.restype = C.c_char_p
     lib.cgpt_launch_count.restype = C.c_longlong
     _declare(lib)
+    lib.cgpt_answer_hash.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.cgpt_answer_hash.restype = C.c_uint64
     _lib = lib
     return lib
 
@@ -72,7 +74,16 @@ def _declare(lib):
 
 
 def _EXTRA_SIGS(vp, i64, i32, f32, f64, u64):
-    return {}
+    u32 = C.c_uint32
+    return {
+        "cgpt_noise_patchify": [vp, vp, u64, u32, u64, i32, f32, vp, vp, i32, i32, i32, vp, i64, vp],
+        "cgpt_noise_image": [vp, vp, u64, u32, u64, i32, f32, vp, vp, i32, i32, i32, i32, i32, vp, vp],
+        "cgpt_answer_labels": [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp],
+        "cgpt_argmax_rows": [vp, i32, i32, i64, i32, vp, vp, vp],
+        "cgpt_label_hist": [vp, i32, i32, vp, vp, vp],
+        "cgpt_certify_tail": [vp, vp, i32, i64, f64, f64, vp, vp, vp],
+        "cgpt_predict_tail": [vp, i32, f64, vp, vp, vp],
+    }
 
 
 def check(rc):
@@ -130,3 +141,131 @@ def gemm(a, w, *, out=None, bias=None, resid=None, act=ACT_NONE, out_dtype=torch
     check(lib.cgpt_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K,
                              C.byref(e), force_bn, stream_ptr()))
     return out
+
+
+# ------------------------------------------------------------------------------- noise
+BLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)   # processors/base_processor.py:17
+BLIP_STD = (0.26862954, 0.26130258, 0.27577711)   # processors/base_processor.py:19
+
+
+def _f3(vals):
+    return (C.c_float * 4)(*[float(v) for v in vals], *([0.0] * (4 - len(vals))))
+
+
+def noise_patchify(x, B, sigma, *, eps=None, seed=0, stream_id=0, first_sample=0,
+                   noise_space=SPACE_NORMALIZED, noise_kind=NOISE_GAUSSIAN,
+                   mean=BLIP_MEAN, std=BLIP_STD, out=None):
+    """K1: x [3,S,S] fp32 -> bf16 patch rows [B*(S/14)^2, 592]."""
+    lib = load()
+    assert x.dtype == torch.float32 and x.dim() == 3 and x.shape[0] == 3 and x.is_contiguous()
+    S = x.shape[-1]
+    assert x.shape[1] == S
+    G = S // 14
+    if eps is not None:
+        assert eps.dtype == torch.float32 and eps.is_contiguous() and tuple(eps.shape) == (B, 3, S, S)
+    if out is None:
+        out = torch.empty(B * G * G, 592, dtype=torch.bfloat16, device=x.device)
+    check(lib.cgpt_noise_patchify(ptr(x), ptr(eps), seed, stream_id, first_sample, B, float(sigma),
+                                  _f3(mean), _f3(std), noise_space, noise_kind, S, ptr(out),
+                                  out.stride(0), stream_ptr()))
+    return out
+
+
+def noise_image(x, B, sigma, *, eps=None, seed=0, stream_id=0, first_sample=0,
+                noise_space=SPACE_NORMALIZED, noise_kind=NOISE_GAUSSIAN, mean=None, std=None,
+                out=None):
+    """Generic path: x [C,H,W] fp32 -> [B,C,H,W] fp32 = x + sigma*eps (optionally normalised)."""
+    lib = load()
+    assert x.dtype == torch.float32 and x.dim() == 3 and x.is_contiguous()
+    Cc, H, W = x.shape
+    if eps is not None:
+        assert eps.dtype == torch.float32 and eps.is_contiguous() and tuple(eps.shape) == (B, Cc, H, W)
+    if out is None:
+        out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=x.device)
+    m = _f3(mean) if mean is not None else None
+    sd = _f3(std) if std is not None else None
+    check(lib.cgpt_noise_image(ptr(x), ptr(eps), seed, stream_id, first_sample, B, float(sigma),
+                               m, sd, noise_space, noise_kind, Cc, H, W, ptr(out), stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------- labels / stats
+def answer_hash(ids, eos_id=2):
+    arr = (C.c_int32 * len(ids))(*[int(i) for i in ids])
+    return int(load().cgpt_answer_hash(arr, len(ids), eos_id))
+
+
+def build_answer_table(entries, eos_id=2, device="cuda"):
+    """entries: iterable of (token_id_sequence, label).  Returns (keys u64-as-i64, vals i32)."""
+    entries = list(entries)
+    cap = 16
+    while cap < 2 * max(1, len(entries)):
+        cap *= 2
+    keys = [0] * cap
+    vals = [-1] * cap
+    for seq, label in entries:
+        h = answer_hash(seq, eos_id)
+        slot = (h ^ (h >> 32)) & 0xffffffff & (cap - 1)
+        while keys[slot] != 0 and keys[slot] != h:
+            slot = (slot + 1) & (cap - 1)
+        if keys[slot] == h and vals[slot] != label:
+            raise ValueError(f"answer table: two labels for one canonical answer {seq}")
+        keys[slot] = h
+        vals[slot] = int(label)
+    import numpy as np
+    k = torch.from_numpy(np.array(keys, dtype=np.uint64).view(np.int64)).to(device)
+    v = torch.tensor(vals, dtype=torch.int32, device=device)
+    return k, v
+
+
+def answer_labels(ids, table_keys, table_vals, other_label, eos_id=2, out=None):
+    lib = load()
+    assert ids.dtype == torch.int32 and ids.dim() == 2 and ids.stride(1) == 1
+    B, max_new = ids.shape
+    if out is None:
+        out = torch.empty(B, dtype=torch.int32, device=ids.device)
+    check(lib.cgpt_answer_labels(ptr(ids), B, max_new, ids.stride(0), eos_id, ptr(table_keys),
+                                 ptr(table_vals), table_keys.numel(), other_label, ptr(out),
+                                 stream_ptr()))
+    return out
+
+
+def argmax_rows(logits, suppress_col=-1, want_margin=False):
+    lib = load()
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    rows, cols = logits.shape
+    idx = torch.empty(rows, dtype=torch.int32, device=logits.device)
+    margin = torch.empty(rows, dtype=torch.float32, device=logits.device) if want_margin else None
+    check(lib.cgpt_argmax_rows(ptr(logits), rows, cols, logits.stride(0), suppress_col, ptr(idx),
+                               ptr(margin), stream_ptr()))
+    return (idx, margin) if want_margin else idx
+
+
+def label_hist(labels, counts, invalid=None):
+    """counts (int64 [num_classes], device) += histogram(labels); asynchronous."""
+    lib = load()
+    assert labels.dtype == torch.int32 and counts.dtype == torch.int64 and labels.is_contiguous()
+    check(lib.cgpt_label_hist(ptr(labels), labels.numel(), counts.numel(), ptr(counts), ptr(invalid),
+                              stream_ptr()))
+    return counts
+
+
+def certify_tail(counts_sel, counts_est, n, alpha, sigma):
+    """Device tail of Smooth.certify; returns (label_dev int32[2], stats_dev f64[3])."""
+    lib = load()
+    assert counts_sel.dtype == torch.int64 and counts_est.dtype == torch.int64
+    lab = torch.empty(2, dtype=torch.int32, device=counts_sel.device)
+    st = torch.empty(3, dtype=torch.float64, device=counts_sel.device)
+    check(lib.cgpt_certify_tail(ptr(counts_sel), ptr(counts_est), counts_sel.numel(), int(n),
+                                float(alpha), float(sigma), ptr(lab), ptr(st), stream_ptr()))
+    return lab, st
+
+
+def predict_tail(counts, alpha):
+    lib = load()
+    assert counts.dtype == torch.int64
+    lab = torch.empty(3, dtype=torch.int32, device=counts.device)
+    st = torch.empty(3, dtype=torch.float64, device=counts.device)
+    check(lib.cgpt_predict_tail(ptr(counts), counts.numel(), float(alpha), ptr(lab), ptr(st),
+                                stream_ptr()))
+    return lab, st

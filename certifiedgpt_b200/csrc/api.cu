@@ -29,4 +29,47 @@ int cgpt_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M
   return gemm_bf16(A, lda, W, ldw, M, N, K, epi, force_bn, (cudaStream_t)stream);
 }
 
+int cgpt_noise_patchify(const float* x, const float* eps, uint64_t seed, uint32_t stream_id,
+                        uint64_t first_sample, int B, float sigma, const float* mean3,
+                        const float* std3, int noise_space, int noise_kind, int img_size,
+                        void* out_patches, int64_t ld_out, void* stream) {
+  return noise_patchify(x, eps, seed, stream_id, first_sample, B, sigma, mean3, std3, noise_space,
+                        noise_kind, img_size, out_patches, ld_out, (cudaStream_t)stream);
+}
+int cgpt_noise_image(const float* x, const float* eps, uint64_t seed, uint32_t stream_id,
+                     uint64_t first_sample, int B, float sigma, const float* mean3,
+                     const float* std3, int noise_space, int noise_kind, int channels, int height,
+                     int width, float* out, void* stream) {
+  return noise_image(x, eps, seed, stream_id, first_sample, B, sigma, mean3, std3, noise_space,
+                     noise_kind, channels, height, width, out, (cudaStream_t)stream);
+}
+int cgpt_answer_labels(const int32_t* ids, int B, int max_new, int ld_ids, int eos_id,
+                       const uint64_t* table_keys, const int32_t* table_vals, int capacity,
+                       int other_label, int32_t* labels, void* stream) {
+  return answer_labels(ids, B, max_new, ld_ids, eos_id, table_keys, table_vals, capacity,
+                       other_label, labels, (cudaStream_t)stream);
+}
+uint64_t cgpt_answer_hash(const int32_t* ids, int n, int eos_id) {
+  return answer_hash_host(ids, n, eos_id);
+}
+int cgpt_argmax_rows(const float* logits, int rows, int cols, int64_t ld, int suppress_col,
+                     int32_t* out_idx, float* out_margin, void* stream) {
+  return argmax_rows(logits, rows, cols, ld, suppress_col, out_idx, out_margin, (cudaStream_t)stream);
+}
+int cgpt_label_hist(const int32_t* labels, int B, int num_classes, int64_t* counts,
+                    int32_t* invalid, void* stream) {
+  return label_hist(labels, B, num_classes, (long long*)counts, invalid, (cudaStream_t)stream);
+}
+int cgpt_certify_tail(const int64_t* counts_sel, const int64_t* counts_est, int num_classes,
+                      int64_t n, double alpha, double sigma, int32_t* out_label,
+                      double* out_stats, void* stream) {
+  return certify_tail((const long long*)counts_sel, (const long long*)counts_est, num_classes, n,
+                      alpha, sigma, out_label, out_stats, (cudaStream_t)stream);
+}
+int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int32_t* out_label,
+                      double* out_stats, void* stream) {
+  return predict_tail((const long long*)counts, num_classes, alpha, out_label, out_stats,
+                      (cudaStream_t)stream);
+}
+
 }  // extern "C"

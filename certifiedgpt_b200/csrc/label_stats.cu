@@ -1,0 +1,358 @@
+// K16-K18: answer-token-sequence -> label hash, label histogram, and the statistics tail of
+// Smooth.certify / Smooth.predict, all on the device so the Monte-Carlo loop needs no per-batch
+// host sync (the reference does predictions.cpu().numpy() + a Python counting loop per batch,
+// randomized_smoothing/smoothing.py:98,101-105).
+//
+//   answer_labels : generated ids -> canonical token sequence -> 64-bit FNV-1a -> open-addressing
+//                   table lookup -> class id (unknown answers -> `other_label`).  Canonicalisation
+//                   restates minigpt_base.py:438-446 at token level: stop at the first EOS,
+//                   drop special ids (<unk>=0, <s>=1, </s>=2: decode(skip_special_tokens=True)).
+//   argmax_rows   : logits.argmax(1) (+ top-2 margin) for generic classifiers / the lm_head
+//   label_hist    : counts[label] += 1 with warp-aggregated (match.any) 64-bit atomics
+//   certify_tail  : cAHat = argmax(counts_sel) (lowest index on ties, smoothing.py:46),
+//                   nA = counts_est[cAHat], pABar = BetaInv(alpha; nA, n-nA+1)  (:51,:117),
+//                   pABar < 0.5 ? (ABSTAIN, 0) : (cAHat, sigma * PhiInv(pABar))  (:52-56)
+//   predict_tail  : top-2 counts, two-sided exact binomial test p=0.5 vs alpha (:73-79)
+#include <math.h>
+#include "common.cuh"
+#include "ops.h"
+
+namespace cgpt {
+
+// ------------------------------------------------------------------ answer hash
+__host__ __device__ __forceinline__ uint64_t fnv1a_push(uint64_t h, uint32_t v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h ^= (v >> (8 * i)) & 0xffu;
+    h *= 0x100000001b3ull;
+  }
+  return h;
+}
+
+__global__ void answer_labels_kernel(const int* __restrict__ ids, int B, int max_new, int ld_ids,
+                                     int eos_id, const uint64_t* __restrict__ keys,
+                                     const int* __restrict__ vals, int cap_mask, int other_label,
+                                     int* __restrict__ labels) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  uint64_t h = 0xcbf29ce484222325ull;
+  int len = 0;
+  for (int t = 0; t < max_new; ++t) {
+    const int id = ids[static_cast<long long>(b) * ld_ids + t];
+    if (id == eos_id) break;
+    if (id == 0 || id == 1 || id == 2) continue;
+    h = fnv1a_push(h, static_cast<uint32_t>(id));
+    ++len;
+  }
+  h = fnv1a_push(h, static_cast<uint32_t>(len));
+  if (h == 0) h = 1;
+  int label = other_label;
+  uint32_t slot = static_cast<uint32_t>(h ^ (h >> 32)) & cap_mask;
+  for (int probe = 0; probe <= cap_mask; ++probe) {
+    const uint64_t k = keys[slot];
+    if (k == h) { label = vals[slot]; break; }
+    if (k == 0) break;
+    slot = (slot + 1) & cap_mask;
+  }
+  labels[b] = label;
+}
+
+// ------------------------------------------------------------------ row argmax (+ margin)
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ logits, int rows,
+                                                          int cols, long long ld, int suppress_col,
+                                                          int* __restrict__ out_idx,
+                                                          float* __restrict__ out_margin) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const float* row = logits + static_cast<long long>(r) * ld;
+  float best = -INFINITY, second = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float v = row[c];
+    if (c == suppress_col) v = -INFINITY;
+    if (v > best || (v == best && c < bi)) { second = best; best = v; bi = c; }
+    else if (v > second) second = v;
+  }
+  // warp then block reduction of (best, idx, second); lowest index wins ties (torch.argmax)
+  auto merge = [](float& b1, int& i1, float& s1, float b2, int i2, float s2) {
+    if (b2 > b1 || (b2 == b1 && i2 < i1)) { s1 = fmaxf(b1, s2); b1 = b2; i1 = i2; }
+    else { s1 = fmaxf(s1, b2); }
+  };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    const float s2 = __shfl_xor_sync(0xffffffffu, second, o);
+    merge(best, bi, second, b2, i2, s2);
+  }
+  __shared__ float sb[8], ss[8];
+  __shared__ int si[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sb[w] = best; si[w] = bi; ss[w] = second; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (blockDim.x >> 5); ++k) merge(best, bi, second, sb[k], si[k], ss[k]);
+    out_idx[r] = bi;
+    if (out_margin) out_margin[r] = best - second;
+  }
+}
+
+// ------------------------------------------------------------------ histogram
+__global__ void __launch_bounds__(256) label_hist_kernel(const int* __restrict__ labels, int B,
+                                                         int num_classes,
+                                                         unsigned long long* __restrict__ counts,
+                                                         int* __restrict__ invalid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < B;
+  int label = active ? labels[i] : -1;
+  const bool ok = active && label >= 0 && label < num_classes;
+  if (active && !ok && invalid) atomicAdd(invalid, 1);
+  const unsigned mask = __ballot_sync(0xffffffffu, ok);
+  if (ok) {
+    const unsigned peers = __match_any_sync(mask, label);
+    const int leader = __ffs(peers) - 1;
+    if ((threadIdx.x & 31) == leader)
+      atomicAdd(&counts[label], static_cast<unsigned long long>(__popc(peers)));
+  }
+}
+
+// ------------------------------------------------------------------ fp64 statistics
+// Phi^-1: Wichura's AS241 PPND16 (relative accuracy ~1e-16)
+__device__ double ppnd16(double p) {
+  const double q = p - 0.5;
+  double r, val;
+  if (fabs(q) <= 0.425) {
+    r = 0.180625 - q * q;
+    val = q * (((((((2.5090809287301226727e3 * r + 3.3430575583588128105e4) * r + 6.7265770927008700853e4) * r +
+                   4.5921953931549871457e4) * r + 1.3731693765509461125e4) * r + 1.9715909503065514427e3) * r +
+                 1.3314166789178437745e2) * r + 3.3871328727963666080e0) /
+          (((((((5.2264952788528545610e3 * r + 2.8729085735721942674e4) * r + 3.9307895800092710610e4) * r +
+               2.1213794301586595867e4) * r + 5.3941960214247511077e3) * r + 6.8718700749205790830e2) * r +
+            4.2313330701600911252e1) * r + 1.0);
+    return val;
+  }
+  r = q < 0 ? p : 1.0 - p;
+  r = sqrt(-log(r));
+  if (r <= 5.0) {
+    r -= 1.6;
+    val = (((((((7.74545014278341407640e-4 * r + 2.27238449892691845833e-2) * r + 2.41780725177450611770e-1) * r +
+               1.27045825245236838258e0) * r + 3.64784832476320460504e0) * r + 5.76949722146069140550e0) * r +
+            4.63033784615654529590e0) * r + 1.42343711074968357734e0) /
+          (((((((1.05075007164441684324e-9 * r + 5.47593808499534494600e-4) * r + 1.51986665636164571966e-2) * r +
+               1.48103976427480074590e-1) * r + 6.89767334985100004550e-1) * r + 1.67638483018380384940e0) * r +
+            2.05319162663775882187e0) * r + 1.0);
+  } else {
+    r -= 5.0;
+    val = (((((((2.01033439929228813265e-7 * r + 2.71155556874348757815e-5) * r + 1.24266094738807843860e-3) * r +
+               2.65321895265761230930e-2) * r + 2.96560571828504891230e-1) * r + 1.78482653991729133580e0) * r +
+            5.46378491116411436990e0) * r + 6.65790464350110377720e0) /
+          (((((((2.04426310338993978564e-15 * r + 1.42151175831644588870e-7) * r + 1.84631831751005468180e-5) * r +
+               7.86869131145613259100e-4) * r + 1.48753612908506148525e-2) * r + 1.36929880922735805310e-1) * r +
+            5.99832206555887937690e-1) * r + 1.0);
+  }
+  return q < 0 ? -val : val;
+}
+
+// block-wide deterministic sum (fixed tree), result valid in every thread
+__device__ double block_sum(double v, double* sh) {
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int k = 0; k < (blockDim.x >> 5); ++k) t += sh[k];
+  return t;
+}
+
+// P[Bin(n, p) >= k0]  =  I_p(k0, n-k0+1), summed term by term in fp64
+__device__ double binom_upper_tail(long long n, long long k0, double p, double* sh) {
+  const double lp = log(p), lq = log1p(-p);
+  const double lgn = lgamma(static_cast<double>(n) + 1.0);
+  double acc = 0.0;
+  for (long long k = k0 + threadIdx.x; k <= n; k += blockDim.x) {
+    const double lt = lgn - lgamma(static_cast<double>(k) + 1.0) - lgamma(static_cast<double>(n - k) + 1.0) +
+                      static_cast<double>(k) * lp + static_cast<double>(n - k) * lq;
+    acc += exp(lt);
+  }
+  return block_sum(acc, sh);
+}
+
+// Clopper-Pearson lower bound: the p with P[Bin(n,p) >= nA] = alpha
+__device__ double clopper_pearson_lower(long long nA, long long n, double alpha, double* sh) {
+  if (nA <= 0) return 0.0;
+  if (nA >= n) return pow(alpha, 1.0 / static_cast<double>(n));
+  double lo = 0.0, hi = 1.0;
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid <= lo || mid >= hi) break;
+    const double f = binom_upper_tail(n, nA, mid, sh);
+    if (f < alpha) lo = mid; else hi = mid;
+  }
+  return 0.5 * (lo + hi);
+}
+
+__global__ void __launch_bounds__(256) certify_tail_kernel(const long long* __restrict__ counts_sel,
+                                                           const long long* __restrict__ counts_est,
+                                                           int num_classes, long long n, double alpha,
+                                                           double sigma, int* __restrict__ out_label,
+                                                           double* __restrict__ out_stats) {
+  __shared__ double sh[8];
+  __shared__ long long s_best[256];
+  __shared__ int s_idx[256];
+  long long best = -1;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < num_classes; c += blockDim.x) {
+    const long long v = counts_sel[c];
+    if (v > best) { best = v; bi = c; }  // ascending c per thread: first max kept
+  }
+  s_best[threadIdx.x] = best; s_idx[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const long long b2 = s_best[threadIdx.x + o];
+      const int i2 = s_idx[threadIdx.x + o];
+      if (b2 > s_best[threadIdx.x] || (b2 == s_best[threadIdx.x] && i2 < s_idx[threadIdx.x])) {
+        s_best[threadIdx.x] = b2; s_idx[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  const int cA = s_idx[0];
+  const long long nA = counts_est[cA];
+  const double pABar = clopper_pearson_lower(nA, n, alpha, sh);
+  if (threadIdx.x == 0) {
+    if (pABar < 0.5) {
+      out_label[0] = -1;
+      out_stats[0] = 0.0;
+    } else {
+      out_label[0] = cA;
+      out_stats[0] = sigma * ppnd16(pABar);
+    }
+    out_label[1] = cA;
+    out_stats[1] = pABar;
+    out_stats[2] = static_cast<double>(nA);
+  }
+}
+
+__global__ void __launch_bounds__(256) predict_tail_kernel(const long long* __restrict__ counts,
+                                                           int num_classes, double alpha,
+                                                           int* __restrict__ out_label,
+                                                           double* __restrict__ out_stats) {
+  __shared__ double sh[8];
+  __shared__ long long s_best[256];
+  __shared__ int s_idx[256];
+  int top[2] = {-1, -1};
+  long long topc[2] = {0, 0};
+  for (int pass = 0; pass < 2; ++pass) {
+    long long best = -1;
+    int bi = 0x7fffffff;
+    for (int c = threadIdx.x; c < num_classes; c += blockDim.x) {
+      if (pass == 1 && c == top[0]) continue;
+      const long long v = counts[c];
+      if (v > best) { best = v; bi = c; }
+    }
+    s_best[threadIdx.x] = best; s_idx[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        const long long b2 = s_best[threadIdx.x + o];
+        const int i2 = s_idx[threadIdx.x + o];
+        if (b2 > s_best[threadIdx.x] || (b2 == s_best[threadIdx.x] && i2 < s_idx[threadIdx.x])) {
+          s_best[threadIdx.x] = b2; s_idx[threadIdx.x] = i2;
+        }
+      }
+      __syncthreads();
+    }
+    top[pass] = s_idx[0];
+    topc[pass] = s_best[0] < 0 ? 0 : s_best[0];
+    __syncthreads();
+  }
+  // two-sided exact binomial test with p = 0.5 (symmetric): 2 * P[X >= max(c1,c2)], capped at 1
+  const long long c1 = topc[0], c2 = topc[1], m = c1 + c2;
+  double pval = 1.0;
+  if (c1 != c2 && m > 0) {
+    const long long hi = c1 > c2 ? c1 : c2;
+    const double tail = binom_upper_tail(m, hi, 0.5, sh);
+    pval = fmin(1.0, 2.0 * tail);
+  }
+  if (threadIdx.x == 0) {
+    out_label[0] = (pval > alpha) ? -1 : top[0];
+    out_label[1] = top[0];
+    out_label[2] = top[1];
+    out_stats[0] = pval;
+    out_stats[1] = static_cast<double>(c1);
+    out_stats[2] = static_cast<double>(c2);
+  }
+}
+
+// ------------------------------------------------------------------ host wrappers
+int answer_labels(const int* ids, int B, int max_new, int ld_ids, int eos_id, const uint64_t* keys,
+                  const int* vals, int capacity, int other_label, int* labels, cudaStream_t stream) {
+  CGPT_REQUIRE(B > 0 && max_new > 0 && ld_ids >= max_new, "answer_labels: bad shape B=%d max_new=%d ld=%d",
+               B, max_new, ld_ids);
+  CGPT_REQUIRE(capacity > 0 && (capacity & (capacity - 1)) == 0,
+               "answer_labels: table capacity must be a power of two (got %d)", capacity);
+  answer_labels_kernel<<<(B + 127) / 128, 128, 0, stream>>>(ids, B, max_new, ld_ids, eos_id, keys, vals,
+                                                           capacity - 1, other_label, labels);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int argmax_rows(const float* logits, int rows, int cols, long long ld, int suppress_col, int* out_idx,
+                float* out_margin, cudaStream_t stream) {
+  CGPT_REQUIRE(rows > 0 && cols > 0 && ld >= cols, "argmax_rows: bad shape rows=%d cols=%d", rows, cols);
+  argmax_rows_kernel<<<rows, 256, 0, stream>>>(logits, rows, cols, ld, suppress_col, out_idx, out_margin);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int label_hist(const int* labels, int B, int num_classes, long long* counts, int* invalid,
+               cudaStream_t stream) {
+  CGPT_REQUIRE(B >= 0 && num_classes > 0, "label_hist: bad shape B=%d classes=%d", B, num_classes);
+  if (B == 0) return 0;
+  label_hist_kernel<<<(B + 255) / 256, 256, 0, stream>>>(
+      labels, B, num_classes, reinterpret_cast<unsigned long long*>(counts), invalid);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int certify_tail(const long long* counts_sel, const long long* counts_est, int num_classes, long long n,
+                 double alpha, double sigma, int* out_label, double* out_stats, cudaStream_t stream) {
+  CGPT_REQUIRE(num_classes > 0 && n > 0 && alpha > 0.0 && alpha < 1.0,
+               "certify_tail: bad arguments classes=%d n=%lld alpha=%g", num_classes, n, alpha);
+  certify_tail_kernel<<<1, 256, 0, stream>>>(counts_sel, counts_est, num_classes, n, alpha, sigma,
+                                             out_label, out_stats);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int predict_tail(const long long* counts, int num_classes, double alpha, int* out_label,
+                 double* out_stats, cudaStream_t stream) {
+  CGPT_REQUIRE(num_classes > 0 && alpha > 0.0 && alpha < 1.0, "predict_tail: bad arguments");
+  predict_tail_kernel<<<1, 256, 0, stream>>>(counts, num_classes, alpha, out_label, out_stats);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+uint64_t answer_hash_host(const int* ids, int n, int eos_id) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  int len = 0;
+  for (int t = 0; t < n; ++t) {
+    const int id = ids[t];
+    if (id == eos_id) break;
+    if (id == 0 || id == 1 || id == 2) continue;
+    h = fnv1a_push(h, static_cast<uint32_t>(id));
+    ++len;
+  }
+  h = fnv1a_push(h, static_cast<uint32_t>(len));
+  if (h == 0) h = 1;
+  return h;
+}
+
+}  // namespace cgpt

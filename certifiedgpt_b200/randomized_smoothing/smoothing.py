@@ -1,0 +1,176 @@
+"""Drop-in `Smooth` (reference: randomized_smoothing/smoothing.py:13-117, Cohen et al.).
+
+Same constructor, methods, return types and ABSTAIN convention as the reference, but the
+Monte-Carlo loop runs on the device through libcgpt.so (include/cgpt.h):
+
+  reference (smoothing.py:91-98, per batch)            here
+  ---------------------------------------------------  ----------------------------------------
+  x.repeat + randn_like*sigma + add  (7 fp32 passes)   one fused Philox noise kernel (K1)
+  base_classifier(batch).argmax(1)                     fused MiniGPT-4 engine, or any nn.Module
+  predictions.cpu().numpy()  (sync per batch)          labels stay on the device
+  _count_arr Python loop                               warp-aggregated histogram kernel
+  scipy/statsmodels tail on the host                   fp64 device tail kernel, ONE D2H read
+
+Extras (keyword-only, all optional): `seed`, `noise_space`, `noise_kind`, `process_group`
+(shards the N draws across ranks; one int64 all-reduce per _sample_noise) and
+`inject_noise()` for parity tests on identical noise.
+
+There is no CPU path: `x` must be a CUDA tensor and libcgpt.so must be built.
+"""
+from math import ceil
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+_SPACE = {"normalized": L.SPACE_NORMALIZED, "pixel": L.SPACE_PIXEL}
+_KIND = {"gaussian": L.NOISE_GAUSSIAN, "uniform": L.NOISE_UNIFORM}
+
+
+class Smooth(object):
+    """A smoothed classifier g"""
+
+    # to abstain, Smooth returns this int (smoothing.py:17)
+    ABSTAIN = -1
+
+    def __init__(self, base_classifier, num_classes: int, sigma: float, *, seed: int = 0,
+                 noise_space: str = "normalized", noise_kind: str = "gaussian",
+                 mean=L.BLIP_MEAN, std=L.BLIP_STD, process_group=None):
+        """
+        :param base_classifier: maps [batch x channel x height x width] to [batch x num_classes]
+               (any torch.nn.Module), or a fused engine exposing `noisy_labels(...)`
+        :param num_classes:
+        :param sigma: the noise level hyperparameter
+        """
+        self.base_classifier = base_classifier
+        self.num_classes = num_classes
+        self.sigma = sigma
+        self.seed = int(seed)
+        self.noise_space = _SPACE[noise_space]
+        self.noise_kind = _KIND[noise_kind]
+        self.mean, self.std = tuple(mean), tuple(std)
+        self.process_group = process_group
+        self.image_id = 0          # Philox stream id; bumped per certify/predict call
+        self._cursor = 0           # global sample index inside the current call
+        self._injected = None
+        self.last_counts = None    # device counts of the last _sample_noise (diagnostics)
+        self.last_invalid = None
+        L.load()
+
+    # ------------------------------------------------------------------ parity hook
+    def inject_noise(self, eps):
+        """Use these standard draws instead of Philox: tensor [n_total, C, H, W] (fp32, CUDA) or
+        callable(first, count) -> tensor.  Consumed by global sample index; None restores Philox."""
+        self._injected = eps
+
+    # ------------------------------------------------------------------ reference API
+    def certify(self, x: torch.tensor, n0: int, n: int, alpha: float, batch_size: int) -> (int, float):
+        """Monte Carlo certification (smoothing.py:29-56).  Returns (class, radius) or (ABSTAIN, 0.0)."""
+        self._eval()
+        self._cursor = 0
+        counts_selection = self._sample_noise_device(x, n0, batch_size)
+        counts_estimation = self._sample_noise_device(x, n, batch_size)
+        lab, st = L.certify_tail(counts_selection, counts_estimation, n, alpha, self.sigma)
+        label = int(lab[0].item())         # the one device->host read of the call
+        radius = float(st[0].item())
+        self.last_cAHat = int(lab[1].item())
+        self.last_pABar = float(st[1].item())
+        self.last_counts_selection = counts_selection
+        self.last_counts_estimation = counts_estimation
+        self.image_id += 1
+        if label == Smooth.ABSTAIN:
+            return Smooth.ABSTAIN, 0.0
+        return label, radius
+
+    def predict(self, x: torch.tensor, n: int, alpha: float, batch_size: int) -> int:
+        """Monte Carlo prediction with the top-2 binomial test (smoothing.py:58-79)."""
+        self._eval()
+        self._cursor = 0
+        counts = self._sample_noise_device(x, n, batch_size)
+        lab, st = L.predict_tail(counts, alpha)
+        label = int(lab[0].item())
+        self.last_pvalue = float(st[0].item())
+        self.image_id += 1
+        return label
+
+    def _sample_noise(self, x: torch.tensor, num: int, batch_size) -> np.ndarray:
+        """Per-class counts of the base classifier under noise (smoothing.py:81-99)."""
+        return self._sample_noise_device(x, num, batch_size).cpu().numpy()
+
+    def _count_arr(self, arr, length: int) -> np.ndarray:
+        """Histogram of predictions (smoothing.py:101-105), on the device."""
+        t = torch.as_tensor(np.asarray(arr), dtype=torch.int32).cuda()
+        counts = torch.zeros(length, dtype=torch.int64, device=t.device)
+        L.label_hist(t.contiguous(), counts)
+        return counts.cpu().numpy()
+
+    def _lower_confidence_bound(self, NA: int, N: int, alpha: float) -> float:
+        """Clopper-Pearson (1 - alpha) lower bound (smoothing.py:107-117), fp64 on the device."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        sel = torch.ones(1, dtype=torch.int64, device=dev)
+        est = torch.full((1,), int(NA), dtype=torch.int64, device=dev)
+        _, st = L.certify_tail(sel, est, N, alpha, 1.0)
+        return float(st[1].item())
+
+    # ------------------------------------------------------------------ device loop
+    def _eval(self):
+        ev = getattr(self.base_classifier, "eval", None)
+        if callable(ev):
+            ev()  # smoothing.py:42,71
+
+    def _rank_world(self):
+        pg = self.process_group
+        if pg is None:
+            return 0, 1
+        import torch.distributed as dist
+        return dist.get_rank(pg if pg is not True else None), dist.get_world_size(pg if pg is not True else None)
+
+    def _eps_for(self, first, count):
+        if self._injected is None:
+            return None
+        if callable(self._injected):
+            e = self._injected(first, count)
+        else:
+            e = self._injected[first:first + count]
+        assert e.shape[0] == count, "injected noise exhausted"
+        return e.contiguous()
+
+    def _sample_noise_device(self, x, num: int, batch_size) -> torch.Tensor:
+        if not (isinstance(x, torch.Tensor) and x.is_cuda):
+            raise L.CgptError("Smooth: x must be a CUDA tensor (no CPU path exists)")
+        x = x.detach().to(torch.float32).contiguous()
+        dev = x.device
+        rank, world = self._rank_world()
+        # this rank's contiguous slice of the global sample range [cursor, cursor + num)
+        base = self._cursor
+        lo = base + (num * rank) // world
+        hi = base + (num * (rank + 1)) // world
+        self._cursor += num
+        counts = torch.zeros(self.num_classes, dtype=torch.int64, device=dev)
+        invalid = torch.zeros(1, dtype=torch.int32, device=dev)
+        fused = getattr(self.base_classifier, "noisy_labels", None)
+        with torch.no_grad():
+            first = lo
+            for _ in range(ceil((hi - lo) / batch_size)):
+                this_batch_size = min(batch_size, hi - first)
+                eps = self._eps_for(first, this_batch_size)
+                kw = dict(eps=eps, seed=self.seed, stream_id=self.image_id, first_sample=first,
+                          noise_space=self.noise_space, noise_kind=self.noise_kind)
+                if fused is not None:
+                    labels = fused(x, this_batch_size, self.sigma, mean=self.mean, std=self.std, **kw)
+                else:
+                    mean = self.mean if self.noise_space == L.SPACE_PIXEL else None
+                    std = self.std if self.noise_space == L.SPACE_PIXEL else None
+                    batch = L.noise_image(x, this_batch_size, self.sigma, mean=mean, std=std, **kw)
+                    logits = self.base_classifier(batch)
+                    labels = L.argmax_rows(logits.float().contiguous())
+                L.label_hist(labels, counts, invalid)
+                first += this_batch_size
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM,
+                            group=None if self.process_group is True else self.process_group)
+        self.last_counts = counts
+        self.last_invalid = invalid
+        return counts

@@ -67,6 +67,52 @@ typedef struct cgpt_gemm_epilogue {
 int cgpt_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                    const cgpt_gemm_epilogue* epi, int force_bn, void* stream);
 
+/* ---------------------------------------------------------------- K1 fused noise kernel
+ * out_patches[b*G*G + py*G + px, c*196 + ky*14 + kx] (bf16, ld_out >= 592, cols 588..591 zero)
+ *   = Normalize?( x[c, py*14+ky, px*14+kx] + sigma * eps_b[...] ),  G = img_size/14.
+ * eps == NULL: Philox4x32-10 keyed by (seed; element group, first_sample + b, stream_id), so the
+ * draw of a sample does not depend on batch size or world size; eps != NULL: injected standard
+ * draws [B,3,S,S] fp32 (parity runs).
+ * Replaces smoothing.py:95-97 (x.repeat, randn_like*sigma, add), base_processor.py:17-34
+ * (Normalize) and the unfold of eva_vit.py:202-209. */
+int cgpt_noise_patchify(const float* x, const float* eps, uint64_t seed, uint32_t stream_id,
+                        uint64_t first_sample, int B, float sigma, const float* mean3,
+                        const float* std3, int noise_space, int noise_kind, int img_size,
+                        void* out_patches, int64_t ld_out, void* stream);
+/* same draw, NCHW fp32 output for an arbitrary torch base_classifier (smoothing.py:95-97) */
+int cgpt_noise_image(const float* x, const float* eps, uint64_t seed, uint32_t stream_id,
+                     uint64_t first_sample, int B, float sigma, const float* mean3,
+                     const float* std3, int noise_space, int noise_kind, int channels, int height,
+                     int width, float* out, void* stream);
+
+/* ---------------------------------------------------------------- labels, histogram, tails
+ * cgpt_answer_labels: generated ids [B, ld_ids] -> class id through an open-addressing table of
+ * 64-bit FNV-1a hashes of canonical answer token sequences (stop at first eos_id, drop ids
+ * 0,1,2); unknown -> other_label.  Token-level restatement of minigpt_base.py:438-446 +
+ * agents/minigpt4_eval_agent.py:102 (the reference has no answer->class map).
+ * cgpt_answer_hash is the host-side hash used to build the table. */
+int cgpt_answer_labels(const int32_t* ids, int B, int max_new, int ld_ids, int eos_id,
+                       const uint64_t* table_keys, const int32_t* table_vals, int capacity,
+                       int other_label, int32_t* labels, void* stream);
+uint64_t cgpt_answer_hash(const int32_t* ids, int n, int eos_id);
+/* logits.argmax(1) with lowest-index tie rule (smoothing.py:97) and optional top-2 margin;
+ * suppress_col >= 0 masks one column (HF min_length: EOS suppressed on the first new token) */
+int cgpt_argmax_rows(const float* logits, int rows, int cols, int64_t ld, int suppress_col,
+                     int32_t* out_idx, float* out_margin, void* stream);
+/* counts[label] += 1  (smoothing.py:98,101-105), no host sync; labels outside [0,num_classes)
+ * are not counted and are tallied in *invalid when non-NULL */
+int cgpt_label_hist(const int32_t* labels, int B, int num_classes, int64_t* counts,
+                    int32_t* invalid, void* stream);
+/* smoothing.py:46-56.  out_label[0] = class or -1 (ABSTAIN), out_label[1] = cAHat;
+ * out_stats[0] = radius, [1] = pABar, [2] = nA */
+int cgpt_certify_tail(const int64_t* counts_sel, const int64_t* counts_est, int num_classes,
+                      int64_t n, double alpha, double sigma, int32_t* out_label,
+                      double* out_stats, void* stream);
+/* smoothing.py:73-79.  out_label[0] = class or -1, [1],[2] = top-2 classes;
+ * out_stats[0] = p-value, [1],[2] = top-2 counts */
+int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int32_t* out_label,
+                      double* out_stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,102 @@
+"""GPU parity: drop-in Smooth (generic nn.Module path) vs the oracle on identical injected noise."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import smoothing_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+class Toy(torch.nn.Module):
+    """fp32 linear classifier: both sides compute the same logits up to summation order."""
+
+    def __init__(self, classes, shape, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.w = torch.nn.Parameter(torch.randn(classes, int(np.prod(shape)), generator=g) / 10)
+
+    def forward(self, x):
+        return x.flatten(1).double() @ self.w.t().double()
+
+
+def _pair(classes=6, shape=(3, 16, 16), sigma=0.5, n_total=1200, seed=0):
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    model = Toy(classes, shape, seed)
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(seed + 1))
+    eps = torch.randn(n_total, *shape, generator=torch.Generator().manual_seed(1234))
+    cur = {"base": 0}
+
+    def noise_fn(drawn, count, batch):
+        return eps[cur["base"] + drawn: cur["base"] + drawn + count]
+
+    oracle = so.SmoothOracle(model, classes, sigma, noise_fn=noise_fn)
+    ours = Smooth(model.cuda(), classes, sigma)
+    ours.inject_noise(eps.cuda())
+    return oracle, ours, x, cur, model
+
+
+def test_sample_noise_counts_match_oracle():
+    oracle, ours, x, cur, model = _pair()
+    ref = oracle._sample_noise(x, 500, 64)
+    model.cuda()
+    ours._cursor = 0
+    got = ours._sample_noise(x.cuda(), 500, 64)
+    model.cpu()
+    safe = np.array(oracle.last_margins) > 1e-6
+    assert safe.all()
+    assert got.dtype.kind == "i" and np.array_equal(got, ref)
+    ours._cursor = 0
+    model.cuda()
+    assert np.array_equal(ours._sample_noise(x.cuda(), 500, 500), ref)  # batch size irrelevant
+
+
+@pytest.mark.parametrize("sigma,seed", [(0.25, 0), (0.5, 1), (1.0, 2)])
+def test_certify_matches_oracle(sigma, seed):
+    oracle, ours, x, cur, model = _pair(sigma=sigma, seed=seed)
+    n0, n = 100, 1000
+    model.cpu()
+    cur["base"] = 0
+    sel = oracle._sample_noise(x, n0, 128)
+    cur["base"] = n0
+    est = oracle._sample_noise(x, n, 128)
+    ref_label, ref_radius = so.certify_tail(sel, est, n, 0.001, sigma)
+    model.cuda()
+    label, radius = ours.certify(x.cuda(), n0, n, 0.001, 128)
+    assert np.array_equal(ours.last_counts_selection.cpu().numpy(), sel)
+    assert np.array_equal(ours.last_counts_estimation.cpu().numpy(), est)
+    assert label == ref_label
+    assert radius == pytest.approx(ref_radius, rel=1e-9)
+    assert isinstance(label, int) and isinstance(radius, float)
+
+
+def test_predict_matches_oracle():
+    oracle, ours, x, cur, model = _pair(sigma=0.5, seed=3)
+    model.cpu()
+    cur["base"] = 0
+    ref = oracle.predict(x, 100, 0.001, 32)
+    model.cuda()
+    got = ours.predict(x.cuda(), 100, 0.001, 32)
+    assert got == ref
+
+
+def test_philox_path_runs_and_is_reproducible():
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    model = Toy(4, (3, 16, 16)).cuda()
+    x = torch.rand(3, 16, 16).cuda()
+    a = Smooth(model, 4, 0.5, seed=7)
+    b = Smooth(model, 4, 0.5, seed=7)
+    ca = a._sample_noise(x, 300, 64)
+    cb = b._sample_noise(x, 300, 300)
+    assert ca.sum() == 300 and np.array_equal(ca, cb)
+    c = Smooth(model, 4, 0.5, seed=8)._sample_noise(x, 300, 64)
+    assert c.sum() == 300
+
+
+def test_helpers_match_reference_semantics():
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    s = Smooth(torch.nn.Identity(), 5, 0.25)
+    assert s._count_arr(np.array([0, 4, 4, 2]), 5).tolist() == [1, 0, 1, 0, 2]
+    assert s._lower_confidence_bound(990, 1000, 0.001) == pytest.approx(0.9760361871553114, rel=1e-9)
+    assert s._lower_confidence_bound(0, 1000, 0.001) == 0.0
+    assert Smooth.ABSTAIN == -1
