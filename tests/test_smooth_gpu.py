@@ -30,8 +30,9 @@ def _pair(classes=6, shape=(3, 16, 16), sigma=0.5, n_total=1200, seed=0):
     def noise_fn(drawn, count, batch):
         return eps[cur["base"] + drawn: cur["base"] + drawn + count]
 
+    import copy
     oracle = so.SmoothOracle(model, classes, sigma, noise_fn=noise_fn)
-    ours = Smooth(model.cuda(), classes, sigma)
+    ours = Smooth(copy.deepcopy(model).cuda(), classes, sigma)
     ours.inject_noise(eps.cuda())
     return oracle, ours, x, cur, model
 
@@ -39,15 +40,12 @@ def _pair(classes=6, shape=(3, 16, 16), sigma=0.5, n_total=1200, seed=0):
 def test_sample_noise_counts_match_oracle():
     oracle, ours, x, cur, model = _pair()
     ref = oracle._sample_noise(x, 500, 64)
-    model.cuda()
     ours._cursor = 0
     got = ours._sample_noise(x.cuda(), 500, 64)
-    model.cpu()
     safe = np.array(oracle.last_margins) > 1e-6
     assert safe.all()
     assert got.dtype.kind == "i" and np.array_equal(got, ref)
     ours._cursor = 0
-    model.cuda()
     assert np.array_equal(ours._sample_noise(x.cuda(), 500, 500), ref)  # batch size irrelevant
 
 
@@ -55,13 +53,11 @@ def test_sample_noise_counts_match_oracle():
 def test_certify_matches_oracle(sigma, seed):
     oracle, ours, x, cur, model = _pair(sigma=sigma, seed=seed)
     n0, n = 100, 1000
-    model.cpu()
     cur["base"] = 0
     sel = oracle._sample_noise(x, n0, 128)
     cur["base"] = n0
     est = oracle._sample_noise(x, n, 128)
     ref_label, ref_radius = so.certify_tail(sel, est, n, 0.001, sigma)
-    model.cuda()
     label, radius = ours.certify(x.cuda(), n0, n, 0.001, 128)
     assert np.array_equal(ours.last_counts_selection.cpu().numpy(), sel)
     assert np.array_equal(ours.last_counts_estimation.cpu().numpy(), est)
@@ -72,10 +68,8 @@ def test_certify_matches_oracle(sigma, seed):
 
 def test_predict_matches_oracle():
     oracle, ours, x, cur, model = _pair(sigma=0.5, seed=3)
-    model.cpu()
     cur["base"] = 0
     ref = oracle.predict(x, 100, 0.001, 32)
-    model.cuda()
     got = ours.predict(x.cuda(), 100, 0.001, 32)
     assert got == ref
 
