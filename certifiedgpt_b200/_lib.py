@@ -33,6 +33,18 @@ class GemmEpilogue(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int64), ("q_rows_per_batch", C.c_int),
+        ("k", C.c_void_p), ("v", C.c_void_p), ("ldk", C.c_int64), ("ldv", C.c_int64),
+        ("kv_rows_per_batch", C.c_int),
+        ("kp", C.c_void_p), ("vp", C.c_void_p), ("ldkp", C.c_int64), ("ldvp", C.c_int64), ("P", C.c_int),
+        ("o", C.c_void_p), ("ldo", C.c_int64),
+        ("B", C.c_int), ("H", C.c_int), ("Tq", C.c_int), ("Tk", C.c_int), ("head_dim", C.c_int),
+        ("scale", C.c_float), ("causal", C.c_int), ("decode_kernel", C.c_int),
+    ]
+
+
 _lib = None
 
 
@@ -83,6 +95,11 @@ def _EXTRA_SIGS(vp, i64, i32, f32, f64, u64):
         "cgpt_label_hist": [vp, i32, i32, vp, vp, vp],
         "cgpt_certify_tail": [vp, vp, i32, i64, f64, f64, vp, vp, vp],
         "cgpt_predict_tail": [vp, i32, f64, vp, vp, vp],
+        "cgpt_greedy_step": [vp, i32, vp, vp, i32, i32, i32, i32, vp, vp],
+        "cgpt_norm_rows": [vp, i64, i32, vp, vp, f32, i32, i32, vp, i64, i32, i32, i32, i32, i32, vp],
+        "cgpt_attention": [C.POINTER(AttnArgs), vp],
+        "cgpt_rope_split": [vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, i32, i32, vp],
+        "cgpt_gather_rows": [vp, i64, vp, i32, i32, i32, vp, i64, i32, i32, i32, i32, vp],
     }
 
 
@@ -269,3 +286,61 @@ def predict_tail(counts, alpha):
     check(lib.cgpt_predict_tail(ptr(counts), counts.numel(), float(alpha), ptr(lab), ptr(st),
                                 stream_ptr()))
     return lab, st
+
+
+# ------------------------------------------------------------------------------- model ops
+def _dt(t):
+    return DT_F32 if t.dtype == torch.float32 else DT_BF16
+
+
+def norm_rows(x, gamma, beta, eps, out, *, rms=False, rows=None, gather=None):
+    """LayerNorm / RMSNorm of rows of x ([M, D], fp32 or bf16) into out ([rows, D])."""
+    lib = load()
+    D = x.shape[-1]
+    rows = out.shape[0] if rows is None else rows
+    gp, gs, go = gather if gather is not None else (0, 0, 0)
+    check(lib.cgpt_norm_rows(ptr(x), x.stride(0), _dt(x), ptr(gamma), ptr(beta), float(eps), rows, D,
+                             ptr(out), out.stride(0), _dt(out), 1 if rms else 0, gp, gs, go, stream_ptr()))
+    return out
+
+
+def attention(q, k, v, o, *, B, H, Tq, Tk, head_dim, scale, q_rows_per_batch=None,
+              kv_rows_per_batch=None, causal=False, kp=None, vp=None, P=0, decode=False):
+    """q/k/v/o are 2-D bf16 views whose column 0 is head 0 (e.g. slices of a fused QKV buffer)."""
+    lib = load()
+    a = AttnArgs()
+    a.q = q.data_ptr(); a.ldq = q.stride(0); a.q_rows_per_batch = q_rows_per_batch or Tq
+    a.k = k.data_ptr(); a.v = v.data_ptr(); a.ldk = k.stride(0); a.ldv = v.stride(0)
+    a.kv_rows_per_batch = kv_rows_per_batch or (Tk - P)
+    if P > 0:
+        a.kp = kp.data_ptr(); a.vp = vp.data_ptr(); a.ldkp = kp.stride(0); a.ldvp = vp.stride(0)
+    a.P = P
+    a.o = o.data_ptr(); a.ldo = o.stride(0)
+    a.B, a.H, a.Tq, a.Tk, a.head_dim = B, H, Tq, Tk, head_dim
+    a.scale = float(scale); a.causal = 1 if causal else 0; a.decode_kernel = 1 if decode else 0
+    check(lib.cgpt_attention(C.byref(a), stream_ptr()))
+    return o
+
+
+def rope_split(qkv, T, H, head_dim, pos0, cos_t, sin_t, kcache, vcache, cache_rows_per_batch, cache_row0):
+    lib = load()
+    check(lib.cgpt_rope_split(ptr(qkv), qkv.stride(0), qkv.shape[0], T, H, head_dim, pos0, ptr(cos_t),
+                              ptr(sin_t), ptr(kcache), ptr(vcache), kcache.stride(-2),
+                              cache_rows_per_batch, cache_row0, stream_ptr()))
+
+
+def gather_rows(table, ids, rows, out, *, id_period=None, remap=None):
+    lib = load()
+    D = table.shape[1]
+    if id_period is None:
+        id_period = ids.numel() if ids is not None else table.shape[0]
+    rp, rs, ro = remap if remap is not None else (0, 0, 0)
+    check(lib.cgpt_gather_rows(ptr(table), table.stride(0), ptr(ids), id_period, rows, D, ptr(out),
+                               out.stride(0), _dt(out), rp, rs, ro, stream_ptr()))
+    return out
+
+
+def greedy_step(next_idx, finished, ids_out, t, eos_id, pad_id, unfinished_count=None):
+    lib = load()
+    check(lib.cgpt_greedy_step(ptr(next_idx), next_idx.numel(), ptr(finished), ptr(ids_out),
+                               ids_out.stride(0), t, eos_id, pad_id, ptr(unfinished_count), stream_ptr()))

@@ -56,6 +56,11 @@ int cgpt_argmax_rows(const float* logits, int rows, int cols, int64_t ld, int su
                      int32_t* out_idx, float* out_margin, void* stream) {
   return argmax_rows(logits, rows, cols, ld, suppress_col, out_idx, out_margin, (cudaStream_t)stream);
 }
+int cgpt_greedy_step(const int32_t* next_idx, int B, int32_t* finished, int32_t* ids_out, int ld, int t,
+                     int eos_id, int pad_id, int32_t* unfinished_count, void* stream) {
+  return greedy_step(next_idx, B, finished, ids_out, ld, t, eos_id, pad_id, unfinished_count,
+                     (cudaStream_t)stream);
+}
 int cgpt_label_hist(const int32_t* labels, int B, int num_classes, int64_t* counts,
                     int32_t* invalid, void* stream) {
   return label_hist(labels, B, num_classes, (long long*)counts, invalid, (cudaStream_t)stream);
@@ -70,6 +75,26 @@ int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int3
                       double* out_stats, void* stream) {
   return predict_tail((const long long*)counts, num_classes, alpha, out_label, out_stats,
                       (cudaStream_t)stream);
+}
+
+int cgpt_norm_rows(const void* x, int64_t ldx, int in_dtype, const float* gamma, const float* beta,
+                   float eps, int rows, int D, void* out, int64_t ldo, int out_dtype, int rms,
+                   int in_row_period, int in_row_stride, int in_row_offset, void* stream) {
+  return norm_rows(x, ldx, in_dtype, gamma, beta, eps, rows, D, out, ldo, out_dtype, rms, in_row_period,
+                   in_row_stride, in_row_offset, (cudaStream_t)stream);
+}
+int cgpt_attention(const cgpt_attn_args* args, void* stream) { return attention(args, (cudaStream_t)stream); }
+int cgpt_rope_split(void* qkv, int64_t ld, int rows, int T, int H, int head_dim, int pos0,
+                    const float* cos_table, const float* sin_table, void* kcache, void* vcache,
+                    int64_t ld_cache, int cache_rows_per_batch, int cache_row0, void* stream) {
+  return rope_split(qkv, ld, rows, T, H, head_dim, pos0, cos_table, sin_table, kcache, vcache, ld_cache,
+                    cache_rows_per_batch, cache_row0, (cudaStream_t)stream);
+}
+int cgpt_gather_rows(const void* table, int64_t ldt, const int32_t* ids, int id_period, int rows, int D,
+                     void* out, int64_t ldo, int out_dtype, int remap_period, int remap_stride,
+                     int remap_offset, void* stream) {
+  return gather_rows(table, ldt, ids, id_period, rows, D, out, ldo, out_dtype, remap_period, remap_stride,
+                     remap_offset, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,351 @@
+// Attention cores of the three towers on the smoothing path:
+//   - EVA ViT self-attention, T=257, 16 heads x 88, no mask        (eva_vit.py:133-150)
+//   - Q-Former self (32x32) and cross (32x257) attention, 12 x 64    (Qformer.py:195-275)
+//   - Llama causal prefill with a batch-shared prompt-prefix K/V     (HF LlamaAttention)
+//   - Llama single-token decode against the per-sample KV cache
+//
+// flash_attn_kernel: one CTA = 64 query rows of one (batch, head); 4 warps x 16 rows;
+// K/V streamed in 64-row tiles through a double-buffered cp.async pipeline; QK^T and PV on
+// mma.sync.m16n8k16 bf16 with fp32 online softmax.  Attention is 2.8 % of the ViT FLOPs at
+// 224 px, so this legacy-tensor-path kernel is not on the roofline-critical path; the GEMMs are.
+// The K/V row index space is [shared prefix rows | per-batch rows]: rows < P are read from a
+// batch-invariant buffer (the "<s>[INST] <Img>" prompt prefix), the rest from this batch's rows.
+#include "common.cuh"
+#include "ops.h"
+
+namespace cgpt {
+
+struct AttnParams {
+  const __nv_bfloat16* q; long long ldq; int q_rows_per_batch;
+  const __nv_bfloat16* k; const __nv_bfloat16* v; long long ldk, ldv; int kv_rows_per_batch;
+  const __nv_bfloat16* kp; const __nv_bfloat16* vp; long long ldkp, ldvp; int P;
+  __nv_bfloat16* o; long long ldo;
+  int Tq, Tk;          // valid query rows / total key rows (prefix included)
+  int head_dim;        // real head dim (64, 88, 128)
+  float scale_log2e;   // softmax scale * log2(e)
+  int causal;          // query i sees keys <= i + (Tk - Tq)
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int FA_BM = 64, FA_BN = 64, FA_THREADS = 128;
+
+template <int HD>
+__device__ __forceinline__ void load_rows_tile(uint32_t smem_tile, const __nv_bfloat16* base, long long ld,
+                                               int row0, int nrows_valid, int head_dim,
+                                               const __nv_bfloat16* pbase, long long pld, int P) {
+  // 64 rows x HD cols, 16-byte chunks; rows >= nrows_valid and cols >= head_dim are zero-filled
+  constexpr int CH = HD / 8;
+  constexpr int LDS = HD + 8;
+  for (int i = threadIdx.x; i < FA_BN * CH; i += FA_THREADS) {
+    const int r = i / CH, c = i - r * CH;
+    const int row = row0 + r;
+    const bool valid = row < nrows_valid && c * 8 < head_dim;
+    const __nv_bfloat16* src = base;
+    if (valid) src = (row < P) ? pbase + row * pld + c * 8 : base + static_cast<long long>(row - P) * ld + c * 8;
+    cp_async16(smem_tile + (r * LDS + c * 8) * 2, src, valid);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(AttnParams p) {
+  constexpr int LDS = HD + 8;
+  constexpr int KSTEPS = HD / 16;
+  constexpr int DTILES = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t sQ = smem_u32(smem_raw);
+  const uint32_t sK = sQ + FA_BM * LDS * 2;           // 2 buffers
+  const uint32_t sV = sK + 2 * FA_BN * LDS * 2;       // 2 buffers
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  const __nv_bfloat16* qbase = p.q + static_cast<long long>(b) * p.q_rows_per_batch * p.ldq + h * p.head_dim;
+  const __nv_bfloat16* kbase = p.k + static_cast<long long>(b) * p.kv_rows_per_batch * p.ldk + h * p.head_dim;
+  const __nv_bfloat16* vbase = p.v + static_cast<long long>(b) * p.kv_rows_per_batch * p.ldv + h * p.head_dim;
+  const __nv_bfloat16* kpbase = p.kp ? p.kp + h * p.head_dim : nullptr;
+  const __nv_bfloat16* vpbase = p.vp ? p.vp + h * p.head_dim : nullptr;
+
+  const int q0 = qb * FA_BM;
+  const int offs = p.Tk - p.Tq;
+  int n_tiles = (p.Tk + FA_BN - 1) / FA_BN;
+  if (p.causal) {
+    const int last_q = min(q0 + FA_BM, p.Tq) - 1;
+    n_tiles = min(n_tiles, (last_q + offs) / FA_BN + 1);
+  }
+
+  load_rows_tile<HD>(sQ, qbase, p.ldq, q0, p.Tq, p.head_dim, nullptr, 0, 0);
+  load_rows_tile<HD>(sK, kbase, p.ldk, 0, p.Tk, p.head_dim, kpbase, p.ldkp, p.P);
+  load_rows_tile<HD>(sV, vbase, p.ldv, 0, p.Tk, p.head_dim, vpbase, p.ldvp, p.P);
+  cp_async_commit();
+
+  uint32_t qf[KSTEPS][4];
+  float o_acc[DTILES][4];
+#pragma unroll
+  for (int i = 0; i < DTILES; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const bool warp_active = q0 + warp * 16 < p.Tq;
+
+  for (int j = 0; j < n_tiles; ++j) {
+    const int buf = j & 1;
+    if (j + 1 < n_tiles) {
+      load_rows_tile<HD>(sK + (buf ^ 1) * FA_BN * LDS * 2, kbase, p.ldk, (j + 1) * FA_BN, p.Tk, p.head_dim,
+                         kpbase, p.ldkp, p.P);
+      load_rows_tile<HD>(sV + (buf ^ 1) * FA_BN * LDS * 2, vbase, p.ldv, (j + 1) * FA_BN, p.Tk, p.head_dim,
+                         vpbase, p.ldvp, p.P);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (j == 0) {
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint32_t addr = sQ + ((warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8) * 2;
+        ldmatrix_x4(addr, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+      }
+    }
+    if (warp_active) {
+      const uint32_t kt = sK + buf * FA_BN * LDS * 2;
+      const uint32_t vt = sV + buf * FA_BN * LDS * 2;
+      float s[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {  // pairs of 8-wide key tiles
+          uint32_t b0, b1, b2, b3;
+          const uint32_t addr = kt + ((np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8) * 2;
+          ldmatrix_x4(addr, b0, b1, b2, b3);
+          mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+          mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+        }
+      }
+      // mask + online softmax (rows g and g+8 of this warp's 16)
+      const int qrow0 = q0 + warp * 16 + g;
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = j * FA_BN + nt * 8 + 2 * t + (e & 1);
+          const int qrow = qrow0 + (e >> 1) * 8;
+          const bool ok = col < p.Tk && (!p.causal || col <= qrow + offs);
+          const float val = ok ? s[nt][e] * p.scale_log2e : -INFINITY;
+          s[nt][e] = val;
+          mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        }
+      }
+      float corr[2], m_use[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(m_run[r], mx[r]);
+        m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
+        corr[r] = exp2f(m_run[r] - m_use[r]);
+        m_run[r] = m_new;
+        l_run[r] *= corr[r];
+      }
+      float rs[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = exp2f(s[nt][e] - m_use[e >> 1]);
+          s[nt][e] = pv;
+          rs[e >> 1] += pv;
+        }
+      }
+      l_run[0] += rs[0];
+      l_run[1] += rs[1];
+#pragma unroll
+      for (int dt = 0; dt < DTILES; ++dt) {
+        o_acc[dt][0] *= corr[0]; o_acc[dt][1] *= corr[0];
+        o_acc[dt][2] *= corr[1]; o_acc[dt][3] *= corr[1];
+      }
+      // O += P V
+#pragma unroll
+      for (int kk = 0; kk < FA_BN / 16; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < DTILES / 2; ++dp) {
+          uint32_t b0, b1, b2, b3;
+          const uint32_t addr = vt + ((kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + dp * 16 + (lane >> 4) * 8) * 2;
+          ldmatrix_x4_trans(addr, b0, b1, b2, b3);
+          mma_bf16_16816(o_acc[2 * dp], pa, b0, b1);
+          mma_bf16_16816(o_acc[2 * dp + 1], pa, b2, b3);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  if (warp_active) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
+    const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+    const int qrow0 = q0 + warp * 16 + g;
+    __nv_bfloat16* obase = p.o + static_cast<long long>(b) * p.q_rows_per_batch * p.ldo + h * p.head_dim;
+#pragma unroll
+    for (int dt = 0; dt < DTILES; ++dt) {
+      const int col = dt * 8 + 2 * t;
+      if (col < p.head_dim) {
+        if (qrow0 < p.Tq)
+          *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(qrow0) * p.ldo + col) =
+              pack_bf16x2(o_acc[dt][0] * inv0, o_acc[dt][1] * inv0);
+        if (qrow0 + 8 < p.Tq)
+          *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(qrow0 + 8) * p.ldo + col) =
+              pack_bf16x2(o_acc[dt][2] * inv1, o_acc[dt][3] * inv1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- single-token decode
+// one warp per (batch, head); lanes own key positions for QK^T, then 4 dims each for PV
+template <int HD>
+__global__ void __launch_bounds__(128) decode_attn_kernel(AttnParams p) {
+  constexpr int MAX_CTX = 1024;
+  __shared__ float s_q[4][HD];
+  __shared__ float s_p[4][MAX_CTX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x * 4 + warp, b = blockIdx.y;
+  const __nv_bfloat16* q = p.q + static_cast<long long>(b) * p.q_rows_per_batch * p.ldq + h * HD;
+  const __nv_bfloat16* kbase = p.k + static_cast<long long>(b) * p.kv_rows_per_batch * p.ldk + h * HD;
+  const __nv_bfloat16* vbase = p.v + static_cast<long long>(b) * p.kv_rows_per_batch * p.ldv + h * HD;
+  for (int d = lane; d < HD; d += 32) s_q[warp][d] = __bfloat162float(q[d]);
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int pos = lane; pos < p.Tk; pos += 32) {
+    const __nv_bfloat16* kr = pos < p.P ? p.kp + static_cast<long long>(pos) * p.ldkp + h * HD
+                                        : kbase + static_cast<long long>(pos - p.P) * p.ldk;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 kv = *reinterpret_cast<const uint4*>(kr + c * 8);
+      const float* qq = &s_q[warp][c * 8];
+      acc += bf16_lo(kv.x) * qq[0] + bf16_hi(kv.x) * qq[1] + bf16_lo(kv.y) * qq[2] + bf16_hi(kv.y) * qq[3] +
+             bf16_lo(kv.z) * qq[4] + bf16_hi(kv.z) * qq[5] + bf16_lo(kv.w) * qq[6] + bf16_hi(kv.w) * qq[7];
+    }
+    acc *= p.scale_log2e;
+    s_p[warp][pos] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int pos = lane; pos < p.Tk; pos += 32) {
+    const float e = exp2f(s_p[warp][pos] - mx);
+    s_p[warp][pos] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  constexpr int DPL = HD / 32;  // dims per lane
+  float acc[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+  for (int pos = 0; pos < p.Tk; ++pos) {
+    const __nv_bfloat16* vr = pos < p.P ? p.vp + static_cast<long long>(pos) * p.ldvp + h * HD
+                                        : vbase + static_cast<long long>(pos - p.P) * p.ldv;
+    const float pr = s_p[warp][pos];
+    if (DPL == 4) {
+      const uint2 vv = *reinterpret_cast<const uint2*>(vr + lane * 4);
+      acc[0] += pr * bf16_lo(vv.x); acc[1] += pr * bf16_hi(vv.x);
+      acc[2] += pr * bf16_lo(vv.y); acc[3] += pr * bf16_hi(vv.y);
+    } else {
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) acc[i] += pr * __bfloat162float(vr[lane * DPL + i]);
+    }
+  }
+  __nv_bfloat16* o = p.o + static_cast<long long>(b) * p.q_rows_per_batch * p.ldo + h * HD + lane * DPL;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) o[i] = __float2bfloat16(acc[i] * inv);
+}
+
+// ---------------------------------------------------------------- host
+template <int HD>
+static int launch_flash(const AttnParams& p, int B, int H, cudaStream_t stream) {
+  constexpr int smem = 5 * FA_BM * (HD + 8) * 2;
+  static bool configured = false;
+  if (!configured) {
+    CGPT_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.Tq + FA_BM - 1) / FA_BM, H, B);
+  flash_attn_kernel<HD><<<grid, FA_THREADS, smem, stream>>>(p);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int attention(const cgpt_attn_args* a, cudaStream_t stream) {
+  CGPT_REQUIRE(a != nullptr, "attention: null args");
+  CGPT_REQUIRE(a->B > 0 && a->B <= 65535 && a->H > 0 && a->Tq > 0 && a->Tk > 0,
+               "attention: bad sizes B=%d H=%d Tq=%d Tk=%d", a->B, a->H, a->Tq, a->Tk);
+  CGPT_REQUIRE(a->head_dim % 8 == 0 && a->head_dim <= 128, "attention: head_dim %d unsupported", a->head_dim);
+  CGPT_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 2 == 0,
+               "attention: leading dims must keep 16-byte row alignment");
+  CGPT_REQUIRE(a->P >= 0 && a->P <= a->Tk && (a->P == 0 || (a->kp && a->vp)), "attention: bad prefix");
+  CGPT_REQUIRE(a->Tk - a->P <= a->kv_rows_per_batch && a->Tq <= a->q_rows_per_batch,
+               "attention: rows per batch too small");
+  AttnParams p;
+  p.q = (const __nv_bfloat16*)a->q; p.ldq = a->ldq; p.q_rows_per_batch = a->q_rows_per_batch;
+  p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v; p.ldk = a->ldk; p.ldv = a->ldv;
+  p.kv_rows_per_batch = a->kv_rows_per_batch;
+  p.kp = (const __nv_bfloat16*)a->kp; p.vp = (const __nv_bfloat16*)a->vp; p.ldkp = a->ldkp; p.ldvp = a->ldvp;
+  p.P = a->P;
+  p.o = (__nv_bfloat16*)a->o; p.ldo = a->ldo;
+  p.Tq = a->Tq; p.Tk = a->Tk; p.head_dim = a->head_dim;
+  p.scale_log2e = a->scale * 1.4426950408889634f;
+  p.causal = a->causal;
+  if (a->Tq == 1 && a->decode_kernel) {
+    CGPT_REQUIRE(a->H % 4 == 0 && a->Tk <= 1024, "decode attention: H %% 4 == 0 and Tk <= 1024 required");
+    dim3 grid(a->H / 4, a->B);
+    if (a->head_dim == 128) decode_attn_kernel<128><<<grid, 128, 0, stream>>>(p);
+    else if (a->head_dim == 64) decode_attn_kernel<64><<<grid, 128, 0, stream>>>(p);
+    else if (a->head_dim == 32) decode_attn_kernel<32><<<grid, 128, 0, stream>>>(p);
+    else CGPT_REQUIRE(false, "decode attention: head_dim %d unsupported", a->head_dim);
+    CGPT_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
+  if (a->head_dim <= 32) return launch_flash<32>(p, a->B, a->H, stream);
+  if (a->head_dim <= 64) return launch_flash<64>(p, a->B, a->H, stream);
+  if (a->head_dim <= 96) return launch_flash<96>(p, a->B, a->H, stream);
+  return launch_flash<128>(p, a->B, a->H, stream);
+}
+
+}  // namespace cgpt

@@ -97,6 +97,21 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------ greedy bookkeeping
+// HF greedy search row update: finished rows emit pad; a row finishes when it emits EOS.
+__global__ void greedy_step_kernel(const int* __restrict__ next_idx, int B, int* __restrict__ finished,
+                                   int* __restrict__ ids_out, int ld, int t, int eos_id, int pad_id,
+                                   int* __restrict__ unfinished_count) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int fin = finished[b];
+  const int tok = fin ? pad_id : next_idx[b];
+  ids_out[static_cast<long long>(b) * ld + t] = tok;
+  const int now = fin | (tok == eos_id);
+  finished[b] = now;
+  if (!now && unfinished_count) atomicAdd(unfinished_count, 1);
+}
+
 // ------------------------------------------------------------------ histogram
 __global__ void __launch_bounds__(256) label_hist_kernel(const int* __restrict__ labels, int B,
                                                          int num_classes,
@@ -304,6 +319,16 @@ int argmax_rows(const float* logits, int rows, int cols, long long ld, int suppr
                 float* out_margin, cudaStream_t stream) {
   CGPT_REQUIRE(rows > 0 && cols > 0 && ld >= cols, "argmax_rows: bad shape rows=%d cols=%d", rows, cols);
   argmax_rows_kernel<<<rows, 256, 0, stream>>>(logits, rows, cols, ld, suppress_col, out_idx, out_margin);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int greedy_step(const int* next_idx, int B, int* finished, int* ids_out, int ld, int t, int eos_id,
+                int pad_id, int* unfinished_count, cudaStream_t stream) {
+  CGPT_REQUIRE(B > 0 && t >= 0 && t < ld, "greedy_step: bad arguments B=%d t=%d ld=%d", B, t, ld);
+  greedy_step_kernel<<<(B + 127) / 128, 128, 0, stream>>>(next_idx, B, finished, ids_out, ld, t, eos_id,
+                                                         pad_id, unfinished_count);
   CGPT_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

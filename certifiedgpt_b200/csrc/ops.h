@@ -25,10 +25,22 @@ int answer_labels(const int* ids, int B, int max_new, int ld_ids, int eos_id, co
 uint64_t answer_hash_host(const int* ids, int n, int eos_id);
 int argmax_rows(const float* logits, int rows, int cols, long long ld, int suppress_col, int* out_idx,
                 float* out_margin, cudaStream_t stream);
+int greedy_step(const int* next_idx, int B, int* finished, int* ids_out, int ld, int t, int eos_id,
+                int pad_id, int* unfinished_count, cudaStream_t stream);
 int label_hist(const int* labels, int B, int num_classes, long long* counts, int* invalid,
                cudaStream_t stream);
 int certify_tail(const long long* counts_sel, const long long* counts_est, int num_classes, long long n,
                  double alpha, double sigma, int* out_label, double* out_stats, cudaStream_t stream);
 int predict_tail(const long long* counts, int num_classes, double alpha, int* out_label,
                  double* out_stats, cudaStream_t stream);
+int norm_rows(const void* x, long long ldx, int in_dtype, const float* gamma, const float* beta,
+              float eps, int rows, int D, void* out, long long ldo, int out_dtype, int rms,
+              int in_row_period, int in_row_stride, int in_row_offset, cudaStream_t stream);
+int attention(const cgpt_attn_args* a, cudaStream_t stream);
+int rope_split(void* qkv, long long ld, int rows, int T, int H, int head_dim, int pos0, const float* cos_t,
+               const float* sin_t, void* kcache, void* vcache, long long ldc, int cache_rows_per_batch,
+               int cache_row0, cudaStream_t stream);
+int gather_rows(const void* table, long long ldt, const int* ids, int id_period, int rows, int D, void* out,
+                long long ldo, int out_dtype, int remap_period, int remap_stride, int remap_offset,
+                cudaStream_t stream);
 }  // namespace cgpt

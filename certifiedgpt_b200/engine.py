@@ -1,0 +1,387 @@
+"""MiniGPT-4 noisy-sample classifier engine: the base classifier `Smooth` calls on the B200 path.
+
+Host orchestration (Python/PyTorch for device memory and streams only) over the sm_100a kernels
+of libcgpt.so.  One call of `noisy_labels` = one batch of the reference's hot loop
+(smoothing.py:95-97 -> [missing adapter] -> MiniGPTBase.generate, minigpt_base.py:374-448):
+
+    K1  noise + normalise + patchify                       cgpt_noise_patchify
+    A6  patch embed GEMM (+bias +pos, cls scatter)         cgpt_gemm_bf16 (eva_vit.py:204-210,337-340)
+    A7  39 x [LN, QKV, attention, proj+res, LN, fc1+GELU, fc2+res]   (eva_vit.py:178-181)
+    A8  ln_vision                                           (base_model.py:281-287)
+    A9  Q-Former, 32 queries, cross K/V of all layers in ONE GEMM     (Qformer.py:402-484)
+    A10 llama_proj, written straight into the LLM input rows          (minigpt4.py:141)
+    A11 prompt embedding assembly, text part shared by the batch      (minigpt_base.py:75-89)
+    A12 Llama prefill over [image | question] rows with the shared "<s>[INST] <Img>" prefix KV,
+        greedy decode with EOS bookkeeping                             (minigpt_base.py:414-427)
+    A13 answer -> label hash                                           (minigpt_base.py:438-446)
+
+The residual streams are fp32, GEMM operands bf16, accumulation fp32.
+"""
+import math
+
+import torch
+
+from . import _lib as L
+from .config import ModelConfig
+
+
+def _bf16(t, device):
+    return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class MiniGPT4Engine:
+    cgpt_fused = True
+
+    def __init__(self, cfg: ModelConfig, state_dict, prefix_ids, suffix_ids, answer_table,
+                 num_classes, *, max_new_tokens=20, min_length=1, device="cuda", early_exit=True):
+        L.load()
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.num_classes = int(num_classes)
+        self.other_label = self.num_classes - 1
+        self.max_new_tokens = int(max_new_tokens)
+        self.min_length = int(min_length)
+        self.early_exit = early_exit
+        self.prefix_ids = [int(i) for i in prefix_ids]
+        self.suffix_ids = [int(i) for i in suffix_ids]
+        self.P = len(self.prefix_ids)
+        self.Tp = cfg.qf.n_query + len(self.suffix_ids)      # per-sample prompt rows
+        self.S = self.P + self.Tp                            # full prompt length
+        self.cache_rows = self.Tp + self.max_new_tokens
+        self._pack(state_dict)
+        self.table_keys, self.table_vals = L.build_answer_table(answer_table, cfg.llm.eos_id, self.dev)
+        self._buf = {}
+        self._buf_B = 0
+        self._build_prefix_cache()
+        self.last = {}
+
+    def eval(self):
+        return self
+
+    # ------------------------------------------------------------------ weights
+    def _pack(self, sd):
+        cfg, dev = self.cfg, self.dev
+        v, q, l = cfg.vit, cfg.qf, cfg.llm
+        w = {}
+        pw = sd["visual_encoder.patch_embed.proj.weight"].reshape(v.dim, -1)      # [dim, 588] (c,ky,kx)
+        pwp = torch.zeros(v.dim, 592, dtype=pw.dtype, device=pw.device)
+        pwp[:, :588] = pw
+        w["patch.w"] = _bf16(pwp, dev)
+        w["patch.b"] = _f32(sd["visual_encoder.patch_embed.proj.bias"], dev)
+        pos = sd["visual_encoder.pos_embed"][0]
+        assert pos.shape[0] == v.tokens, "pos_embed does not match image size (interpolate first)"
+        w["pos"] = _f32(pos, dev)
+        w["cls_pos"] = _f32(sd["visual_encoder.cls_token"][0, 0] + pos[0], dev)
+        for i in range(v.depth):
+            p = f"visual_encoder.blocks.{i}."
+            o = f"vit.{i}."
+            w[o + "ln1.w"], w[o + "ln1.b"] = _f32(sd[p + "norm1.weight"], dev), _f32(sd[p + "norm1.bias"], dev)
+            w[o + "qkv.w"] = _bf16(sd[p + "attn.qkv.weight"], dev)
+            w[o + "qkv.b"] = _f32(torch.cat((sd[p + "attn.q_bias"], torch.zeros_like(sd[p + "attn.v_bias"]),
+                                             sd[p + "attn.v_bias"])), dev)         # eva_vit.py:127
+            w[o + "proj.w"], w[o + "proj.b"] = _bf16(sd[p + "attn.proj.weight"], dev), _f32(sd[p + "attn.proj.bias"], dev)
+            w[o + "ln2.w"], w[o + "ln2.b"] = _f32(sd[p + "norm2.weight"], dev), _f32(sd[p + "norm2.bias"], dev)
+            w[o + "fc1.w"], w[o + "fc1.b"] = _bf16(sd[p + "mlp.fc1.weight"], dev), _f32(sd[p + "mlp.fc1.bias"], dev)
+            w[o + "fc2.w"], w[o + "fc2.b"] = _bf16(sd[p + "mlp.fc2.weight"], dev), _f32(sd[p + "mlp.fc2.bias"], dev)
+        w["lnv.w"], w["lnv.b"] = _f32(sd["ln_vision.weight"], dev), _f32(sd["ln_vision.bias"], dev)
+
+        # Q-Former.  K8: LN(query_tokens) is input independent -> folded here (Qformer.py:104-107)
+        qt = sd["query_tokens"][0].float()
+        q0 = torch.nn.functional.layer_norm(qt, (q.hidden,), sd["Qformer.bert.embeddings.LayerNorm.weight"].float(),
+                                            sd["Qformer.bert.embeddings.LayerNorm.bias"].float(), q.eps)
+        w["qf.q0"] = _bf16(q0, dev)
+        ckv_w, ckv_b = [], []
+        for i in range(q.layers):
+            p = f"Qformer.bert.encoder.layer.{i}."
+            o = f"qf.{i}."
+            a = p + "attention."
+            w[o + "qkv.w"] = _bf16(torch.cat([sd[a + f"self.{n}.weight"] for n in ("query", "key", "value")]), dev)
+            w[o + "qkv.b"] = _f32(torch.cat([sd[a + f"self.{n}.bias"] for n in ("query", "key", "value")]), dev)
+            w[o + "ao.w"], w[o + "ao.b"] = _bf16(sd[a + "output.dense.weight"], dev), _f32(sd[a + "output.dense.bias"], dev)
+            w[o + "aln.w"], w[o + "aln.b"] = _f32(sd[a + "output.LayerNorm.weight"], dev), _f32(sd[a + "output.LayerNorm.bias"], dev)
+            if i % q.cross_freq == 0:
+                c = p + "crossattention."
+                w[o + "cq.w"], w[o + "cq.b"] = _bf16(sd[c + "self.query.weight"], dev), _f32(sd[c + "self.query.bias"], dev)
+                ckv_w += [sd[c + "self.key.weight"], sd[c + "self.value.weight"]]
+                ckv_b += [sd[c + "self.key.bias"], sd[c + "self.value.bias"]]
+                w[o + "co.w"], w[o + "co.b"] = _bf16(sd[c + "output.dense.weight"], dev), _f32(sd[c + "output.dense.bias"], dev)
+                w[o + "cln.w"], w[o + "cln.b"] = _f32(sd[c + "output.LayerNorm.weight"], dev), _f32(sd[c + "output.LayerNorm.bias"], dev)
+            w[o + "fi.w"], w[o + "fi.b"] = _bf16(sd[p + "intermediate_query.dense.weight"], dev), _f32(sd[p + "intermediate_query.dense.bias"], dev)
+            w[o + "fo.w"], w[o + "fo.b"] = _bf16(sd[p + "output_query.dense.weight"], dev), _f32(sd[p + "output_query.dense.bias"], dev)
+            w[o + "fln.w"], w[o + "fln.b"] = _f32(sd[p + "output_query.LayerNorm.weight"], dev), _f32(sd[p + "output_query.LayerNorm.bias"], dev)
+        # K10: the cross-attention K/V projections of ALL cross layers as one [n_cross*2*hidden, vit.dim] GEMM
+        w["qf.ckv.w"] = _bf16(torch.cat(ckv_w), dev)
+        w["qf.ckv.b"] = _f32(torch.cat(ckv_b), dev)
+        w["proj.w"], w["proj.b"] = _bf16(sd["llama_proj.weight"], dev), _f32(sd["llama_proj.bias"], dev)
+
+        # Llama
+        w["emb"] = _bf16(sd["llama_model.model.embed_tokens.weight"], dev)
+        for i in range(l.layers):
+            p = f"llama_model.model.layers.{i}."
+            o = f"llm.{i}."
+            w[o + "qkv.w"] = _bf16(torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in ("q", "k", "v")]), dev)
+            w[o + "o.w"] = _bf16(sd[p + "self_attn.o_proj.weight"], dev)
+            gu = torch.stack((sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]), dim=1)
+            w[o + "gu.w"] = _bf16(gu.reshape(2 * l.inter, l.hidden), dev)          # rows (gate_j, up_j) interleaved
+            w[o + "down.w"] = _bf16(sd[p + "mlp.down_proj.weight"], dev)
+            w[o + "n1"] = _f32(sd[p + "input_layernorm.weight"], dev)
+            w[o + "n2"] = _f32(sd[p + "post_attention_layernorm.weight"], dev)
+        w["llm.norm"] = _f32(sd["llama_model.model.norm.weight"], dev)
+        w["llm.head"] = _bf16(sd["llama_model.lm_head.weight"], dev)
+        max_pos = self.S + self.max_new_tokens + 1
+        inv = 1.0 / (l.rope_theta ** (torch.arange(0, l.head_dim, 2, dtype=torch.float32) / l.head_dim))
+        fr = torch.outer(torch.arange(max_pos, dtype=torch.float32), inv)
+        w["rope.cos"], w["rope.sin"] = _f32(fr.cos(), dev), _f32(fr.sin(), dev)
+        self.w = w
+        self.prefix_ids_dev = torch.tensor(self.prefix_ids, dtype=torch.int32, device=dev)
+        self.suffix_ids_dev = torch.tensor(self.suffix_ids, dtype=torch.int32, device=dev)
+
+    # ------------------------------------------------------------------ buffers
+    def _buffers(self, B):
+        if B <= self._buf_B:
+            return self._buf
+        cfg, dev = self.cfg, self.dev
+        v, q, l = cfg.vit, cfg.qf, cfg.llm
+        bf, f32 = torch.bfloat16, torch.float32
+        Mv, Mq, Ml = B * v.tokens, B * q.n_query, B * self.Tp
+        n_cross = len(q.cross_layers())
+
+        def e(*shape, dtype=bf):
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
+        self._buf = None
+        torch.cuda.empty_cache()
+        b = {
+            "patches": e(B * v.grid * v.grid, 592),
+            "v.res": e(Mv, v.dim, dtype=f32), "v.xn": e(Mv, v.dim), "v.qkv": e(Mv, 3 * v.dim),
+            "v.att": e(Mv, v.dim), "v.h": e(Mv, v.mlp), "v.out": e(Mv, v.dim),
+            "q.h": e(Mq, q.hidden), "q.tmp": e(Mq, q.hidden, dtype=f32), "q.qkv": e(Mq, 3 * q.hidden),
+            "q.ctx": e(Mq, q.hidden), "q.cq": e(Mq, q.hidden), "q.ckv": e(Mv, n_cross * 2 * q.hidden),
+            "q.inter": e(Mq, q.inter),
+            "l.res": e(Ml, l.hidden, dtype=f32), "l.xn": e(Ml, l.hidden), "l.qkv": e(Ml, 3 * l.hidden),
+            "l.att": e(Ml, l.hidden), "l.act": e(Ml, l.inter),
+            "l.kc": e(l.layers, B, self.cache_rows, l.hidden), "l.vc": e(l.layers, B, self.cache_rows, l.hidden),
+            "l.last": e(B, l.hidden), "l.logits": e(B, l.vocab, dtype=f32),
+            "d.res": e(B, l.hidden, dtype=f32), "d.xn": e(B, l.hidden), "d.qkv": e(B, 3 * l.hidden),
+            "d.att": e(B, l.hidden), "d.act": e(B, l.inter),
+            "ids": torch.zeros(B, self.max_new_tokens, dtype=torch.int32, device=dev),
+            "finished": torch.zeros(B, dtype=torch.int32, device=dev),
+            "unfinished": torch.zeros(1, dtype=torch.int32, device=dev),
+            "next": torch.zeros(B, dtype=torch.int32, device=dev),
+            "margin": torch.zeros(B, self.max_new_tokens, dtype=f32, device=dev),
+            "labels": torch.zeros(B, dtype=torch.int32, device=dev),
+        }
+        self._buf, self._buf_B = b, B
+        return b
+
+    # ------------------------------------------------------------------ towers
+    def vit_from_patches(self, B, buf, collect=None):
+        """patches (buf['patches']) -> ln_vision(ViT features) in buf['v.out'] [B*T, dim] bf16."""
+        v, w = self.cfg.vit, self.w
+        T, Pn = v.tokens, v.grid * v.grid
+        M = B * T
+        res, xn, qkv, att, h = (buf[k][:M] for k in ("v.res", "v.xn", "v.qkv", "v.att", "v.h"))
+        # A6: conv14 as GEMM; epilogue adds bias + pos_embed[1+p] and scatters row b*Pn+p -> b*T+1+p
+        L.gemm(buf["patches"][:B * Pn], w["patch.w"], bias=w["patch.b"], out=res, row_add=w["pos"],
+               row_period=Pn, row_add_offset=1, remap_stride=T, remap_offset=1)
+        res.view(B, T, v.dim)[:, 0] = w["cls_pos"]                      # cls token + pos[0] (eva_vit.py:337-340)
+        if collect is not None:
+            collect["embed"] = res.view(B, T, v.dim).clone()
+        scale = v.head_dim ** -0.5
+        for i in range(v.depth):
+            o = f"vit.{i}."
+            L.norm_rows(res, w[o + "ln1.w"], w[o + "ln1.b"], v.eps, xn)
+            L.gemm(xn, w[o + "qkv.w"], bias=w[o + "qkv.b"], out=qkv)
+            L.attention(qkv[:, :v.dim], qkv[:, v.dim:2 * v.dim], qkv[:, 2 * v.dim:], att, B=B, H=v.heads,
+                        Tq=T, Tk=T, head_dim=v.head_dim, scale=scale)
+            L.gemm(att, w[o + "proj.w"], bias=w[o + "proj.b"], resid=res, out=res)
+            L.norm_rows(res, w[o + "ln2.w"], w[o + "ln2.b"], v.eps, xn)
+            L.gemm(xn, w[o + "fc1.w"], bias=w[o + "fc1.b"], act=L.ACT_GELU, out=h)
+            L.gemm(h, w[o + "fc2.w"], bias=w[o + "fc2.b"], resid=res, out=res)
+            if collect is not None:
+                collect[f"block{i}"] = res.view(B, T, v.dim).clone()
+        out = buf["v.out"][:M]
+        L.norm_rows(res, w["lnv.w"], w["lnv.b"], self.cfg.ln_vision_eps, out)   # A8
+        if collect is not None:
+            collect["image_embeds"] = out.view(B, T, v.dim).float()
+        return out
+
+    def qformer(self, B, buf, image_embeds, collect=None):
+        """image_embeds [B*T, vit.dim] bf16 -> query outputs buf['q.h'] [B*n_query, hidden] bf16."""
+        cfg, w = self.cfg, self.w
+        v, q = cfg.vit, cfg.qf
+        T, nq, Hd = v.tokens, q.n_query, q.hidden
+        M = B * nq
+        h, tmp, qkv, ctx, cq, inter = (buf[k][:M] for k in ("q.h", "q.tmp", "q.qkv", "q.ctx", "q.cq", "q.inter"))
+        ckv = buf["q.ckv"][:B * T]
+        L.gather_rows(w["qf.q0"], None, M, h, id_period=nq)            # query_tokens.expand(B) (minigpt4.py:133)
+        L.gemm(image_embeds, w["qf.ckv.w"], bias=w["qf.ckv.b"], out=ckv)   # K10: all cross K/V at once
+        scale = 1.0 / math.sqrt(q.head_dim)
+        ci = 0
+        for i in range(q.layers):
+            o = f"qf.{i}."
+            L.gemm(h, w[o + "qkv.w"], bias=w[o + "qkv.b"], out=qkv)
+            L.attention(qkv[:, :Hd], qkv[:, Hd:2 * Hd], qkv[:, 2 * Hd:], ctx, B=B, H=q.heads, Tq=nq, Tk=nq,
+                        head_dim=q.head_dim, scale=scale)
+            L.gemm(ctx, w[o + "ao.w"], bias=w[o + "ao.b"], resid=h, out=tmp)
+            L.norm_rows(tmp, w[o + "aln.w"], w[o + "aln.b"], q.eps, h)
+            if i % q.cross_freq == 0:
+                L.gemm(h, w[o + "cq.w"], bias=w[o + "cq.b"], out=cq)
+                kcol = ci * 2 * Hd
+                L.attention(cq, ckv[:, kcol:kcol + Hd], ckv[:, kcol + Hd:kcol + 2 * Hd], ctx, B=B, H=q.heads,
+                            Tq=nq, Tk=T, head_dim=q.head_dim, scale=scale)
+                L.gemm(ctx, w[o + "co.w"], bias=w[o + "co.b"], resid=h, out=tmp)
+                L.norm_rows(tmp, w[o + "cln.w"], w[o + "cln.b"], q.eps, h)
+                ci += 1
+            L.gemm(h, w[o + "fi.w"], bias=w[o + "fi.b"], act=L.ACT_GELU, out=inter)
+            L.gemm(inter, w[o + "fo.w"], bias=w[o + "fo.b"], resid=h, out=tmp)
+            L.norm_rows(tmp, w[o + "fln.w"], w[o + "fln.b"], q.eps, h)
+            if collect is not None:
+                collect[f"layer{i}"] = h.view(B, nq, Hd).float()
+        return h
+
+    # ------------------------------------------------------------------ Llama
+    def _llm_layers(self, rows, T, B, res, xn, qkv, att, act, kc, vc, pos0, cache_row0, cache_rows,
+                    kp=None, vp=None, P=0, decode=False):
+        l, w = self.cfg.llm, self.w
+        Hd = l.hidden
+        scale = 1.0 / math.sqrt(l.head_dim)
+        for i in range(l.layers):
+            o = f"llm.{i}."
+            L.norm_rows(res, w[o + "n1"], None, l.rms_eps, xn, rms=True)
+            L.gemm(xn, w[o + "qkv.w"], out=qkv)
+            L.rope_split(qkv, T, l.heads, l.head_dim, pos0, w["rope.cos"], w["rope.sin"], kc[i], vc[i],
+                         cache_rows, cache_row0)
+            Tk = P + cache_row0 + T
+            L.attention(qkv[:, :Hd], kc[i].view(-1, Hd), vc[i].view(-1, Hd), att, B=B, H=l.heads, Tq=T, Tk=Tk,
+                        head_dim=l.head_dim, scale=scale, kv_rows_per_batch=cache_rows, causal=True,
+                        kp=None if kp is None else kp[i], vp=None if vp is None else vp[i], P=P, decode=decode)
+            L.gemm(att, w[o + "o.w"], resid=res, out=res)
+            L.norm_rows(res, w[o + "n2"], None, l.rms_eps, xn, rms=True)
+            L.gemm(xn, w[o + "gu.w"], act=L.ACT_SWIGLU, out=act)
+            L.gemm(act, w[o + "down.w"], resid=res, out=res)
+
+    def _build_prefix_cache(self):
+        """K/V of the batch-invariant prompt prefix ("<s>[INST] <Img>", the tokens BEFORE the image),
+        computed once: exact under causal attention."""
+        l, dev, P = self.cfg.llm, self.dev, self.P
+        bf, f32 = torch.bfloat16, torch.float32
+        self.kp = torch.zeros(l.layers, max(P, 1), l.hidden, dtype=bf, device=dev)
+        self.vp = torch.zeros_like(self.kp)
+        if P == 0:
+            return
+        res = torch.empty(P, l.hidden, dtype=f32, device=dev)
+        L.gather_rows(self.w["emb"], self.prefix_ids_dev, P, res)
+        xn = torch.empty(P, l.hidden, dtype=bf, device=dev)
+        qkv = torch.empty(P, 3 * l.hidden, dtype=bf, device=dev)
+        att = torch.empty(P, l.hidden, dtype=bf, device=dev)
+        act = torch.empty(P, l.inter, dtype=bf, device=dev)
+        self._llm_layers(P, P, 1, res, xn, qkv, att, act, self.kp.unsqueeze(1), self.vp.unsqueeze(1),
+                         pos0=0, cache_row0=0, cache_rows=P)
+        torch.cuda.synchronize()
+
+    def llm_generate(self, B, buf, qf_out, collect=None):
+        """qf_out [B*n_query, qf.hidden] bf16 -> generated ids buf['ids'] [B, max_new] int32."""
+        cfg, w = self.cfg, self.w
+        q, l = cfg.qf, cfg.llm
+        nq, Tp, P, Hd = q.n_query, self.Tp, self.P, l.hidden
+        ns = len(self.suffix_ids)
+        M = B * Tp
+        res, xn, qkv, att, act = (buf[k][:M] for k in ("l.res", "l.xn", "l.qkv", "l.att", "l.act"))
+        kc, vc = buf["l.kc"][:, :B], buf["l.vc"][:, :B]
+        # A10/A11: llama_proj output lands in rows [b*Tp, b*Tp+nq); question embeddings broadcast behind it
+        L.gemm(qf_out, w["proj.w"], bias=w["proj.b"], out=res, row_period=nq, remap_stride=Tp, remap_offset=0)
+        if ns > 0:
+            L.gather_rows(w["emb"], self.suffix_ids_dev, B * ns, res, id_period=ns, remap=(ns, Tp, nq))
+        if collect is not None:
+            collect["llm_in"] = res.view(B, Tp, Hd).clone()
+        # A12 prefill: per-sample rows attend to the shared prefix K/V + their own causal rows
+        self._llm_layers(M, Tp, B, res, xn, qkv, att, act, kc, vc, pos0=P, cache_row0=0,
+                         cache_rows=self.cache_rows, kp=self.kp, vp=self.vp, P=P)
+        last, logits = buf["l.last"][:B], buf["l.logits"][:B]
+        ids, fin, unf, nxt = buf["ids"][:B], buf["finished"][:B], buf["unfinished"], buf["next"][:B]
+        margin = buf["margin"][:B]
+        ids.fill_(l.pad_id)
+        fin.zero_()
+        margin.fill_(float("inf"))
+        L.norm_rows(res, w["llm.norm"], None, l.rms_eps, last, rms=True, gather=(1, Tp, Tp - 1))
+        dres, dxn, dqkv, datt, dact = (buf[k][:B] for k in ("d.res", "d.xn", "d.qkv", "d.att", "d.act"))
+        steps = 0
+        for t in range(self.max_new_tokens):
+            L.gemm(last, w["llm.head"], out=logits)
+            if collect is not None and t == 0:
+                collect["first_logits"] = logits.clone()
+            self._argmax(logits, l.eos_id if t < self.min_length else -1, nxt, margin, t)
+            unf.zero_()
+            L.greedy_step(nxt, fin, ids, t, l.eos_id, l.pad_id, unf)
+            steps = t + 1
+            if t == self.max_new_tokens - 1:
+                break
+            if self.early_exit and int(unf.item()) == 0:
+                break
+            # next token: embed, one-row-per-sample pass against the KV cache
+            L.gather_rows(w["emb"], ids[:, t].contiguous(), B, dres, id_period=B)
+            self._llm_layers(B, 1, B, dres, dxn, dqkv, datt, dact, kc, vc, pos0=P + Tp + t,
+                             cache_row0=Tp + t, cache_rows=self.cache_rows, kp=self.kp, vp=self.vp, P=P,
+                             decode=l.head_dim in (32, 64, 128) and l.heads % 4 == 0)
+            L.norm_rows(dres, w["llm.norm"], None, l.rms_eps, last, rms=True)
+        self.last_steps = steps
+        return ids
+
+    def _argmax(self, logits, suppress, nxt, margin, t):
+        lib = L.load()
+        rows, cols = logits.shape
+        mcol = torch.empty(rows, dtype=torch.float32, device=logits.device)
+        L.check(lib.cgpt_argmax_rows(L.ptr(logits), rows, cols, logits.stride(0), suppress, L.ptr(nxt),
+                                     L.ptr(mcol), L.stream_ptr()))
+        margin[:, t] = mcol
+
+    # ------------------------------------------------------------------ public entry points
+    def labels_from_patches(self, B, buf, collect=None):
+        img = self.vit_from_patches(B, buf, collect)
+        qo = self.qformer(B, buf, img, collect)
+        if collect is not None:
+            collect["qformer"] = qo.view(B, self.cfg.qf.n_query, -1).float()
+        ids = self.llm_generate(B, buf, qo, collect)
+        labels = buf["labels"][:B]
+        L.answer_labels(ids, self.table_keys, self.table_vals, self.other_label, self.cfg.llm.eos_id, out=labels)
+        if collect is not None:
+            collect["ids"] = ids.clone()
+            collect["margins"] = buf["margin"][:B].clone()
+            collect["labels"] = labels.clone()
+        return labels
+
+    @torch.no_grad()
+    def noisy_labels(self, x, B, sigma, *, eps=None, seed=0, stream_id=0, first_sample=0,
+                     noise_space=L.SPACE_NORMALIZED, noise_kind=L.NOISE_GAUSSIAN,
+                     mean=L.BLIP_MEAN, std=L.BLIP_STD, collect=None):
+        """One batch of the hot loop: labels[b] = f(x + sigma*eps_b), b = first_sample .. +B."""
+        buf = self._buffers(B)
+        G2 = self.cfg.vit.grid ** 2
+        L.noise_patchify(x, B, sigma, eps=eps, seed=seed, stream_id=stream_id, first_sample=first_sample,
+                         noise_space=noise_space, noise_kind=noise_kind, mean=mean, std=std,
+                         out=buf["patches"][:B * G2])
+        return self.labels_from_patches(B, buf, collect)
+
+    @torch.no_grad()
+    def forward_images(self, images, collect=None):
+        """Deterministic forward of an image batch [B,3,S,S] (already in model input space);
+        used by parity tests and by `__call__`."""
+        B = images.shape[0]
+        buf = self._buffers(B)
+        G2 = self.cfg.vit.grid ** 2
+        for b in range(B):
+            L.noise_patchify(images[b].float().contiguous(), 1, 0.0, eps=None,
+                             out=buf["patches"][b * G2:(b + 1) * G2])
+        return self.labels_from_patches(B, buf, collect)
+
+    def __call__(self, images):
+        """nn.Module-style contract of smoothing.py:21: [B,C,H,W] -> one-hot logits [B,num_classes]."""
+        labels = self.forward_images(images).long()
+        out = torch.zeros(images.shape[0], self.num_classes, device=self.dev)
+        out[torch.arange(images.shape[0], device=self.dev), labels] = 1.0
+        return out

@@ -99,6 +99,10 @@ uint64_t cgpt_answer_hash(const int32_t* ids, int n, int eos_id);
  * suppress_col >= 0 masks one column (HF min_length: EOS suppressed on the first new token) */
 int cgpt_argmax_rows(const float* logits, int rows, int cols, int64_t ld, int suppress_col,
                      int32_t* out_idx, float* out_margin, void* stream);
+/* one step of HF greedy search bookkeeping (generate call, minigpt_base.py:414-427): finished rows
+ * emit pad_id, a row finishes on eos_id; *unfinished_count += rows still running (for early exit) */
+int cgpt_greedy_step(const int32_t* next_idx, int B, int32_t* finished, int32_t* ids_out, int ld, int t,
+                     int eos_id, int pad_id, int32_t* unfinished_count, void* stream);
 /* counts[label] += 1  (smoothing.py:98,101-105), no host sync; labels outside [0,num_classes)
  * are not counted and are tallied in *invalid when non-NULL */
 int cgpt_label_hist(const int32_t* labels, int B, int num_classes, int64_t* counts,
@@ -112,6 +116,49 @@ int cgpt_certify_tail(const int64_t* counts_sel, const int64_t* counts_est, int 
  * out_stats[0] = p-value, [1],[2] = top-2 counts */
 int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int32_t* out_label,
                       double* out_stats, void* stream);
+
+/* ---------------------------------------------------------------- norms
+ * LayerNorm (rms = 0) or RMSNorm (rms = 1) over rows of width D; fp32 statistics.
+ * Replaces nn.LayerNorm in eva_vit.Block (eva_vit.py:162,168; eps 1e-6), ln_vision
+ * (base_model.py:281-287; eps 1e-5), BERT LayerNorms (Qformer.py:66,285-289,367-375; eps 1e-12)
+ * and HF LlamaRMSNorm.  in_row_period > 0 gathers input row
+ * (r / period) * in_row_stride + in_row_offset + r % period (e.g. last token of each sample). */
+int cgpt_norm_rows(const void* x, int64_t ldx, int in_dtype, const float* gamma, const float* beta,
+                   float eps, int rows, int D, void* out, int64_t ldo, int out_dtype, int rms,
+                   int in_row_period, int in_row_stride, int in_row_offset, void* stream);
+
+/* ---------------------------------------------------------------- attention
+ * softmax(scale * Q K^T [+ causal mask]) V per (batch, head), bf16 in/out, fp32 softmax.
+ * Head h occupies columns [h*head_dim, (h+1)*head_dim) of the q/k/v/o rows.  Key rows
+ * [0, P) come from the batch-invariant prefix buffers kp/vp (shared prompt-prefix KV cache),
+ * rows [P, Tk) from this batch's k/v rows.  causal: query i sees keys <= i + (Tk - Tq).
+ * Replaces eva_vit.Attention.forward (eva_vit.py:133-150), BertSelfAttention.forward
+ * (Qformer.py:195-275) and HF LlamaAttention inside generate (minigpt_base.py:414-427). */
+typedef struct cgpt_attn_args {
+  const void* q; int64_t ldq; int q_rows_per_batch;
+  const void* k; const void* v; int64_t ldk; int64_t ldv; int kv_rows_per_batch;
+  const void* kp; const void* vp; int64_t ldkp; int64_t ldvp; int P;
+  void* o; int64_t ldo;
+  int B, H, Tq, Tk, head_dim;
+  float scale;
+  int causal;
+  int decode_kernel; /* Tq == 1: use the single-token KV-cache kernel */
+} cgpt_attn_args;
+int cgpt_attention(const cgpt_attn_args* args, void* stream);
+
+/* ---------------------------------------------------------------- language-head helpers
+ * HF Llama rotary embedding (rotate_half) on the q,k parts of a fused [rows, 3*H*hd] QKV
+ * buffer; q in place, rotated k and v appended to the KV cache at row
+ * b*cache_rows_per_batch + cache_row0 + i (row m = b*T + i, position pos0 + i).
+ * cos/sin tables: fp32 [max_pos, hd/2]. */
+int cgpt_rope_split(void* qkv, int64_t ld, int rows, int T, int H, int head_dim, int pos0,
+                    const float* cos_table, const float* sin_table, void* kcache, void* vcache,
+                    int64_t ld_cache, int cache_rows_per_batch, int cache_row0, void* stream);
+/* out[remap(r)] = table[ids ? ids[r % id_period] : r % id_period]  (embed_tokens gather and
+ * row broadcast: minigpt_base.py:75-89,367-372,399-412; query_tokens.expand minigpt4.py:133) */
+int cgpt_gather_rows(const void* table, int64_t ldt, const int32_t* ids, int id_period, int rows, int D,
+                     void* out, int64_t ldo, int out_dtype, int remap_period, int remap_stride,
+                     int remap_offset, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,100 @@
+"""CPU tests: the model oracle against (a) golden outputs of the reference's own eva_vit.py /
+Qformer.py modules (tests/golden/ref_*.pt, made by tests/golden/make_ref_fixtures.py) and
+(b) this image's transformers.LlamaForCausalLM (the reference's LLM arithmetic is third-party
+transformers; its subclass only changes the loss, modeling_llama.py:65-84)."""
+import os
+
+import pytest
+import torch
+
+from certifiedgpt_b200.config import LlmConfig, ModelConfig, QFormerConfig, VitConfig
+from certifiedgpt_b200.weights import random_state_dict
+from oracle import model_oracle as mo
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = {
+    "tiny": ModelConfig.tiny(),
+    "wide": ModelConfig(vit=VitConfig(img_size=56, depth=1), qf=QFormerConfig(layers=2)),
+}
+
+
+@pytest.mark.parametrize("name", ["tiny", "wide"])
+def test_vit_matches_reference_module(name):
+    ref = torch.load(os.path.join(GOLD, "ref_vit.pt"))[name]
+    cfg = CASES[name]
+    sd = random_state_dict(cfg, seed=11, parts=("vit", "qf"))
+    out = mo.vit_forward(sd, cfg, ref["images"])
+    assert out.shape == ref["features"].shape
+    assert torch.allclose(out, ref["features"], atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["tiny", "wide"])
+def test_qformer_matches_reference_module(name):
+    ref = torch.load(os.path.join(GOLD, "ref_qformer.pt"))[name]
+    cfg = CASES[name]
+    sd = random_state_dict(cfg, seed=11, parts=("vit", "qf"))
+    out = mo.qformer_forward(sd, cfg, ref["image_embeds"])
+    assert torch.allclose(out, ref["last_hidden_state"], atol=2e-5, rtol=1e-5)
+
+
+def _hf_llama(cfg, sd):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    l = cfg.llm
+    hc = LlamaConfig(hidden_size=l.hidden, intermediate_size=l.inter, num_hidden_layers=l.layers,
+                     num_attention_heads=l.heads, num_key_value_heads=l.heads, vocab_size=l.vocab,
+                     rms_norm_eps=l.rms_eps, rope_theta=l.rope_theta, max_position_embeddings=256,
+                     bos_token_id=1, eos_token_id=l.eos_id, pad_token_id=l.pad_id,
+                     attn_implementation="eager", tie_word_embeddings=False)
+    m = LlamaForCausalLM(hc).eval()
+    hsd = {k[len("llama_model."):]: v for k, v in sd.items() if k.startswith("llama_model.")}
+    missing, unexpected = m.load_state_dict(hsd, strict=False)
+    assert not unexpected and all("rotary" in k or "inv_freq" in k for k in missing), (missing, unexpected)
+    return m
+
+
+def test_llama_logits_and_greedy_generate_match_hf():
+    cfg = ModelConfig.tiny()
+    cfg.llm = LlmConfig(hidden=64, layers=2, heads=4, inter=128, vocab=96)
+    sd = random_state_dict(cfg, seed=3)
+    # make EOS reachable so the finished-row / padding semantics are exercised
+    sd["llama_model.lm_head.weight"][cfg.llm.eos_id] *= 3.0
+    hf = _hf_llama(cfg, sd)
+    g = torch.Generator().manual_seed(0)
+    embeds = torch.randn(5, 11, cfg.llm.hidden, generator=g) * 0.3
+    with torch.no_grad():
+        ref_logits = hf(inputs_embeds=embeds).logits[:, -1].float()
+        ref_ids = hf.generate(inputs_embeds=embeds, attention_mask=torch.ones(5, 11, dtype=torch.long),
+                              max_new_tokens=6, num_beams=1, do_sample=False, min_length=1,
+                              top_p=0.9, repetition_penalty=1.0, length_penalty=1, temperature=1.0)
+    ids, first_logits, margins = mo.generate_ids(sd, cfg, embeds, max_new_tokens=6)
+    assert torch.allclose(first_logits, ref_logits, atol=1e-5, rtol=1e-5)
+    assert margins.shape[0] == 5
+    n = ref_ids.shape[1]
+    assert torch.equal(ids[:, :n], ref_ids)
+    assert (ids[:, n:] == cfg.llm.pad_id).all()
+    assert (ids[:, 0] != cfg.llm.eos_id).all()           # min_length=1
+
+
+def test_prompt_embedding_layout_and_adapter():
+    cfg = ModelConfig.tiny()
+    sd = random_state_dict(cfg, seed=4)
+    img = torch.randn(3, cfg.qf.n_query, cfg.llm.hidden)
+    e = mo.build_prompt_embeds(sd, cfg, img, [1, 5, 6], [7, 8, 9, 10])
+    assert e.shape == (3, 3 + cfg.qf.n_query + 4, cfg.llm.hidden)
+    emb = sd["llama_model.model.embed_tokens.weight"]
+    assert torch.equal(e[1, 0], emb[1]) and torch.equal(e[2, 3:3 + cfg.qf.n_query], img[2])
+    assert torch.equal(e[0, -1], emb[10])
+    assert mo.canonical_answer([0, 5, 1, 6, 2, 9]) == (5, 6)
+    assert mo.answer_label([5, 6, 2, 0], {(5, 6): 3}, other_label=9) == 3
+    assert mo.answer_label([6, 5, 2, 0], {(5, 6): 3}, other_label=9) == 9
+
+
+def test_classifier_oracle_end_to_end_tiny():
+    cfg = ModelConfig.tiny()
+    sd = random_state_dict(cfg, seed=5)
+    table = [((t,), t % 7) for t in range(3, cfg.llm.vocab)]
+    clf = mo.MiniGPT4ClassifierOracle(sd, cfg, [1, 4, 5], [6, 7, 8, 9], table, num_classes=8, max_new_tokens=1)
+    x = torch.randn(4, 3, cfg.vit.img_size, cfg.vit.img_size)
+    out = clf(x)
+    assert out.shape == (4, 8) and torch.equal(out.sum(1), torch.ones(4))
+    assert clf.last["ids"].shape == (4, 1)
