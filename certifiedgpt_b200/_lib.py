@@ -125,6 +125,23 @@ def launch_count():
 
 
 # ------------------------------------------------------------------------------- GEMM
+_gemm_prof = None
+
+
+def gemm_profile_start():
+    """Record a CUDA-event pair around every GEMM launch (bench.py roofline measurement)."""
+    global _gemm_prof
+    _gemm_prof = []
+
+
+def gemm_profile_stop():
+    """-> list of (ms, flops, (M, N, K)); synchronises."""
+    global _gemm_prof
+    rec, _gemm_prof = _gemm_prof or [], None
+    torch.cuda.synchronize()
+    return [(s.elapsed_time(e), fl, shp) for s, e, fl, shp in rec]
+
+
 def gemm(a, w, *, out=None, bias=None, resid=None, act=ACT_NONE, out_dtype=torch.bfloat16,
          row_add=None, row_period=0, row_add_offset=0, remap_stride=0, remap_offset=0,
          out_rows=None, force_bn=0, max_ctas=0):
@@ -155,8 +172,14 @@ def gemm(a, w, *, out=None, bias=None, resid=None, act=ACT_NONE, out_dtype=torch
     e.row_period = row_period; e.row_add_offset = row_add_offset
     e.remap_stride = remap_stride; e.remap_offset = remap_offset
     e.max_ctas = max_ctas
+    if _gemm_prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib.cgpt_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K,
                              C.byref(e), force_bn, stream_ptr()))
+    if _gemm_prof is not None:
+        ev1.record()
+        _gemm_prof.append((ev0, ev1, 2.0 * M * N * K, (M, N, K)))
     return out
 
 
