@@ -11,9 +11,10 @@
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma (UMMA 128 x BN x 16), fp32
 //                                accumulators in TMEM, two accumulator stages
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       : tcgen05.ld -> bias / GELU / SwiGLU / residual / pos-embed
-//                                -> bf16 or fp32 global stores, overlapped with the next
-//                                tile's MMAs through the second TMEM stage
+//   warps 4..11 epilogue       : 2 warps per TMEM lane quarter (column halves); software-pipelined
+//                                tcgen05.ld -> bias (staged in smem) / GELU / SwiGLU / residual
+//                                (prefetched) / pos-embed -> bf16 or fp32 global stores, overlapped
+//                                with the next tile's MMAs through the second TMEM stage
 #include "common.cuh"
 #include "ops.h"
 
@@ -22,7 +23,8 @@ namespace cgpt {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
 
 template <int BN>
 struct GemmCfg {
@@ -30,7 +32,7 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 176 ? 5 : 6);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/;
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
   static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
 };
@@ -52,23 +54,59 @@ struct EpiParams {
   int remap_offset;
 };
 
-// process `NC` consecutive accumulator columns of one row and store them
-template <int NC>
-__device__ __forceinline__ void epilogue_store(const uint32_t* acc, const EpiParams& p, int m,
-                                               long long out_row, int n0, int N) {
+// exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16
+// resolution): 2 MUFU + ~12 FP32 ops instead of erff()'s ~28-instruction select chain
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  const float erf_x = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_x);
+}
+
+// residual prefetch: 16 consecutive columns of one row into registers (fp32 values)
+__device__ __forceinline__ void load_resid16(const EpiParams& p, long long out_row, int n0, float* r) {
+  if (p.resid_f32) {
+    const float* src = reinterpret_cast<const float*>(p.resid) + out_row * p.ldr + n0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(src + i);
+      r[i] = b.x; r[i + 1] = b.y; r[i + 2] = b.z; r[i + 3] = b.w;
+    }
+  } else {
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.resid) + out_row * p.ldr + n0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 8) {
+      const uint4 b = *reinterpret_cast<const uint4*>(src + i);
+      r[i] = bf16_lo(b.x); r[i + 1] = bf16_hi(b.x); r[i + 2] = bf16_lo(b.y); r[i + 3] = bf16_hi(b.y);
+      r[i + 4] = bf16_lo(b.z); r[i + 5] = bf16_hi(b.z); r[i + 6] = bf16_lo(b.w); r[i + 7] = bf16_hi(b.w);
+    }
+  }
+}
+
+// process 16 consecutive accumulator columns of one row and store them
+__device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiParams& p, const float* bias_s,
+                                                 const float* resid_r, int m, long long out_row, int n0) {
+  constexpr int NC = 16;
   float v[NC];
 #pragma unroll
   for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]);
   if (p.bias != nullptr) {
 #pragma unroll
     for (int i = 0; i < NC; i += 4) {
-      float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + i);   // smem broadcast
       v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
     }
   }
   if (p.act == CGPT_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < NC; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < NC; ++i) v[i] = gelu_erf_fast(v[i]);
   }
   if (p.act == CGPT_ACT_SWIGLU) {
     // weight rows are interleaved (gate_j, up_j): out[:, j] = silu(gate_j) * up_j
@@ -77,9 +115,7 @@ __device__ __forceinline__ void epilogue_store(const uint32_t* acc, const EpiPar
 #pragma unroll
     for (int i = 0; i < NC / 4; ++i)
       w[i] = pack_bf16x2(silu(v[4 * i]) * v[4 * i + 1], silu(v[4 * i + 2]) * v[4 * i + 3]);
-#pragma unroll
-    for (int i = 0; i < NC / 16; ++i)
-      *reinterpret_cast<uint4*>(o + 8 * i) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
     return;
   }
   if (p.row_add != nullptr) {
@@ -91,24 +127,8 @@ __device__ __forceinline__ void epilogue_store(const uint32_t* acc, const EpiPar
     }
   }
   if (p.resid != nullptr) {
-    if (p.resid_f32) {
-      const float* r = reinterpret_cast<const float*>(p.resid) + out_row * p.ldr + n0;
 #pragma unroll
-      for (int i = 0; i < NC; i += 4) {
-        float4 b = *reinterpret_cast<const float4*>(r + i);
-        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-      }
-    } else {
-      const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.resid) + out_row * p.ldr + n0;
-#pragma unroll
-      for (int i = 0; i < NC; i += 8) {
-        uint4 b = *reinterpret_cast<const uint4*>(r + i);
-        v[i] += bf16_lo(b.x); v[i + 1] += bf16_hi(b.x);
-        v[i + 2] += bf16_lo(b.y); v[i + 3] += bf16_hi(b.y);
-        v[i + 4] += bf16_lo(b.z); v[i + 5] += bf16_hi(b.z);
-        v[i + 6] += bf16_lo(b.w); v[i + 7] += bf16_hi(b.w);
-      }
-    }
+    for (int i = 0; i < NC; ++i) v[i] += resid_r[i];
   }
   if (p.out_f32) {
     float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
@@ -122,6 +142,28 @@ __device__ __forceinline__ void epilogue_store(const uint32_t* acc, const EpiPar
       *reinterpret_cast<uint4*>(o + i) =
           make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
                      pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+  }
+}
+
+// one epilogue warp's share of a tile: chunks [C0, C1) of 16 columns, software pipelined
+template <int C0, int C1>
+__device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams& epi, const float* bias_s,
+                                                int m, long long out_row, bool row_ok, int n_base, int N) {
+  uint32_t r[2][16];
+  float rr[2][16];
+  const bool has_res = epi.resid != nullptr;
+  tmem_ld_x16(t_row + C0 * 16, r[0]);
+  if (has_res && row_ok && n_base + C0 * 16 < N) load_resid16(epi, out_row, n_base + C0 * 16, rr[0]);
+#pragma unroll
+  for (int c = C0; c < C1; ++c) {
+    const int cur = (c - C0) & 1;
+    tmem_ld_wait();
+    if (c + 1 < C1) {
+      tmem_ld_x16(t_row + (c + 1) * 16, r[cur ^ 1]);
+      if (has_res && row_ok && n_base + (c + 1) * 16 < N) load_resid16(epi, out_row, n_base + (c + 1) * 16, rr[cur ^ 1]);
+    }
+    const int n0 = n_base + c * 16;
+    if (row_ok && n0 < N) epilogue_store16(r[cur], epi, bias_s + c * 16, rr[cur], m, out_row, n0);
   }
 }
 
@@ -143,6 +185,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   uint64_t* tmem_full = bars + 2 * STAGES;    // [2] MMA -> epilogue
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* bias_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // [2][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,7 +205,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], EPI_WARPS);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -222,12 +265,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    // ------------------------------------------------------------ epilogue (8 warps)
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32)
+    const int half = (warp - 4) >> 2;      // column half of the tile
+    const int epi_tid = threadIdx.x - 128; // 0..255
+    constexpr int NCH = BN / 16;
+    constexpr int NCH0 = (NCH + 1) / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int n_base = n_blk * BN;
+      float* bias_s = bias_smem + acc * 256;
+      if (epi.bias != nullptr && epi_tid < BN) {
+        const int n = n_base + epi_tid;
+        bias_s[epi_tid] = n < N ? __ldg(epi.bias + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const int m = m_blk * BM + quarter * 32 + lane;
@@ -237,14 +291,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         out_row = (long long)(m / epi.row_period) * epi.remap_stride + epi.remap_offset +
                   (m % epi.row_period);
       const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld_x16(t_row + c * 16, r);
-        tmem_ld_wait();
-        const int n0 = n_blk * BN + c * 16;
-        if (row_ok && n0 < N) epilogue_store<16>(r, epi, m, out_row, n0, N);
-      }
+      if (half == 0) epilogue_chunks<0, NCH0>(t_row, epi, bias_s, m, out_row, row_ok, n_base, N);
+      else           epilogue_chunks<NCH0, NCH>(t_row, epi, bias_s, m, out_row, row_ok, n_base, N);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);

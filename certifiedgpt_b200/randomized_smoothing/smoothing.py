@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
+from ..dist import allreduce_counts, rank_world, shard_range
 
 _SPACE = {"normalized": L.SPACE_NORMALIZED, "pixel": L.SPACE_PIXEL}
 _KIND = {"gaussian": L.NOISE_GAUSSIAN, "uniform": L.NOISE_UNIFORM}
@@ -119,13 +120,6 @@ class Smooth(object):
         if callable(ev):
             ev()  # smoothing.py:42,71
 
-    def _rank_world(self):
-        pg = self.process_group
-        if pg is None:
-            return 0, 1
-        import torch.distributed as dist
-        return dist.get_rank(pg if pg is not True else None), dist.get_world_size(pg if pg is not True else None)
-
     def _eps_for(self, first, count):
         if self._injected is None:
             return None
@@ -141,11 +135,9 @@ class Smooth(object):
             raise L.CgptError("Smooth: x must be a CUDA tensor (no CPU path exists)")
         x = x.detach().to(torch.float32).contiguous()
         dev = x.device
-        rank, world = self._rank_world()
+        rank, world = rank_world(self.process_group)
         # this rank's contiguous slice of the global sample range [cursor, cursor + num)
-        base = self._cursor
-        lo = base + (num * rank) // world
-        hi = base + (num * (rank + 1)) // world
+        lo, hi = shard_range(self._cursor, num, rank, world)
         self._cursor += num
         counts = torch.zeros(self.num_classes, dtype=torch.int64, device=dev)
         invalid = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -168,9 +160,7 @@ class Smooth(object):
                 L.label_hist(labels, counts, invalid)
                 first += this_batch_size
         if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM,
-                            group=None if self.process_group is True else self.process_group)
+            allreduce_counts(counts, self.process_group)   # the only collective on the path
         self.last_counts = counts
         self.last_invalid = invalid
         return counts

@@ -1,0 +1,89 @@
+"""GPU parity at BASELINE.json's full encoder size (EVA ViT-g/14 39L + Q-Former 12L) and
+size-independent properties of the whole path at full MiniGPT-4 shape."""
+import numpy as np
+import pytest
+import torch
+
+from certifiedgpt_b200.config import LlmConfig, ModelConfig
+from certifiedgpt_b200.weights import random_state_dict, round_to_bf16
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def test_full_depth_encoder_within_bf16_tolerance():
+    """39 ViT-g blocks + 12 Q-Former layers deep: error accumulation stays within rel 2e-2."""
+    from certifiedgpt_b200.engine import MiniGPT4Engine
+    cfg = ModelConfig.full(224)
+    cfg.llm = LlmConfig(hidden=512, layers=1, heads=4, inter=1024, vocab=512)
+    sd = round_to_bf16(random_state_dict(cfg, seed=2))
+    table = [((t,), t % 7) for t in range(3, 512)]
+    eng = MiniGPT4Engine(cfg, sd, (1, 5, 6), (7, 8, 9), table, 8, max_new_tokens=1)
+    images = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(3))
+    got = {}
+    eng.forward_images(images.cuda(), collect=got)
+    ref = {}
+    with torch.no_grad():
+        torch.set_num_threads(max(1, torch.get_num_threads()))
+        img = mo.encode_img(sd, cfg, images, collect=ref)
+    for k in ("embed", "block0", "block19", "block38", "image_embeds"):
+        assert _rel(got[k], ref[k]) < 2e-2, k
+    for i in (0, 5, 11):
+        assert _rel(got[f"layer{i}"], ref[f"layer{i}"]) < 2e-2, f"qformer {i}"
+    P = 3
+    assert _rel(got["llm_in"][:, :cfg.qf.n_query], img) < 2e-2
+
+
+@pytest.fixture(scope="module")
+def full_engine():
+    from certifiedgpt_b200.engine import MiniGPT4Engine
+    cfg = ModelConfig.full(224)
+    sd = random_state_dict(cfg, seed=0, device="cuda")
+    g = torch.Generator().manual_seed(7)
+    prefix = [1] + torch.randint(3, 32000, (6,), generator=g).tolist()
+    suffix = torch.randint(3, 32000, (40,), generator=g).tolist()
+    # label = first generated token mod 9 (2-token answers), so the histogram is non-trivial
+    eng = MiniGPT4Engine(cfg, sd, prefix, suffix, [], 10, max_new_tokens=2, device="cuda")
+    del sd
+    torch.cuda.empty_cache()
+    return eng
+
+
+def test_full_size_counts_independent_of_batch_size(full_engine):
+    """Noise is keyed by global sample index and every kernel is row-independent, so the generated
+    ids of 48 draws are bit-identical whether they run as one batch of 48 or batches of 16."""
+    eng = full_engine
+    x = torch.rand(3, 224, 224, generator=torch.Generator().manual_seed(1000)).cuda()
+    c1 = {}
+    eng.noisy_labels(x, 48, 0.25, seed=42, first_sample=0, collect=c1)
+    ids_full = c1["ids"].clone()
+    parts = []
+    for first in (0, 16, 32):
+        c = {}
+        eng.noisy_labels(x, 16, 0.25, seed=42, first_sample=first, collect=c)
+        parts.append(c["ids"].clone())
+    assert torch.equal(ids_full, torch.cat(parts))
+    assert ids_full.shape == (48, 2) and int(ids_full.min()) >= 0 and int(ids_full.max()) < 32000
+    assert (ids_full[:, 0] != 2).all()       # min_length=1: EOS never first
+
+
+def test_full_size_certify_deterministic_and_consistent(full_engine):
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    x = torch.rand(3, 224, 224, generator=torch.Generator().manual_seed(1001)).cuda()
+    a = Smooth(full_engine, 10, 0.25, seed=1)
+    r1 = a.certify(x, 16, 64, 0.001, 64)
+    sel1, est1 = a.last_counts_selection.clone(), a.last_counts_estimation.clone()
+    b = Smooth(full_engine, 10, 0.25, seed=1)
+    r2 = b.certify(x, 16, 64, 0.001, 32)     # different batch size, same seed
+    assert r1 == r2
+    assert torch.equal(sel1, b.last_counts_selection) and torch.equal(est1, b.last_counts_estimation)
+    assert int(sel1.sum()) == 16 and int(est1.sum()) == 64
+    # the tail is consistent with the counts (oracle on the same counts)
+    from oracle import smoothing_oracle as so
+    ref = so.certify_tail(sel1.cpu().numpy(), est1.cpu().numpy(), 64, 0.001, 0.25)
+    assert r1[0] == ref[0] and r1[1] == pytest.approx(ref[1], rel=1e-9)
