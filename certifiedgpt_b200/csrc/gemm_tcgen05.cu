@@ -56,15 +56,28 @@ struct EpiParams {
 
 // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16
 // resolution): 2 MUFU + ~12 FP32 ops instead of erff()'s ~28-instruction select chain
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_fast(float x) {
+  return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+}
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float e = ex2_approx(-1.4426950408889634f * z * z);
   const float erf_abs = fmaf(-p, e, 1.0f);
   const float erf_x = copysignf(erf_abs, x);
   return 0.5f * x * (1.0f + erf_x);
@@ -114,7 +127,7 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
     uint32_t w[NC / 4];
 #pragma unroll
     for (int i = 0; i < NC / 4; ++i)
-      w[i] = pack_bf16x2(silu(v[4 * i]) * v[4 * i + 1], silu(v[4 * i + 2]) * v[4 * i + 3]);
+      w[i] = pack_bf16x2(silu_fast(v[4 * i]) * v[4 * i + 1], silu_fast(v[4 * i + 2]) * v[4 * i + 3]);
     *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
     return;
   }
@@ -145,25 +158,35 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
   }
 }
 
-// one epilogue warp's share of a tile: chunks [C0, C1) of 16 columns, software pipelined
-template <int C0, int C1>
+// one epilogue warp's share of a tile: chunks [c0, c1) of 16 columns.  The TMEM load of the next
+// chunk and its residual prefetch are in flight while the current chunk is processed; the loop is
+// unrolled by exactly 2 (static register double buffer) and NOT further, so the SASS stays small
+// enough for the instruction cache with 8 warps running it.
 __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams& epi, const float* bias_s,
-                                                int m, long long out_row, bool row_ok, int n_base, int N) {
-  uint32_t r[2][16];
-  float rr[2][16];
-  const bool has_res = epi.resid != nullptr;
-  tmem_ld_x16(t_row + C0 * 16, r[0]);
-  if (has_res && row_ok && n_base + C0 * 16 < N) load_resid16(epi, out_row, n_base + C0 * 16, rr[0]);
-#pragma unroll
-  for (int c = C0; c < C1; ++c) {
-    const int cur = (c - C0) & 1;
+                                                int m, long long out_row, bool row_ok, int n_base, int N,
+                                                int c0, int c1) {
+  uint32_t r0[16], r1[16];
+  float rr0[16], rr1[16];
+  const bool has_res = epi.resid != nullptr && row_ok;
+  tmem_ld_x16(t_row + c0 * 16, r0);
+  if (has_res && n_base + c0 * 16 < N) load_resid16(epi, out_row, n_base + c0 * 16, rr0);
+#pragma unroll 1
+  for (int c = c0; c < c1; c += 2) {
     tmem_ld_wait();
-    if (c + 1 < C1) {
-      tmem_ld_x16(t_row + (c + 1) * 16, r[cur ^ 1]);
-      if (has_res && row_ok && n_base + (c + 1) * 16 < N) load_resid16(epi, out_row, n_base + (c + 1) * 16, rr[cur ^ 1]);
+    if (c + 1 < c1) {
+      tmem_ld_x16(t_row + (c + 1) * 16, r1);
+      if (has_res && n_base + (c + 1) * 16 < N) load_resid16(epi, out_row, n_base + (c + 1) * 16, rr1);
     }
-    const int n0 = n_base + c * 16;
-    if (row_ok && n0 < N) epilogue_store16(r[cur], epi, bias_s + c * 16, rr[cur], m, out_row, n0);
+    if (row_ok && n_base + c * 16 < N) epilogue_store16(r0, epi, bias_s + c * 16, rr0, m, out_row, n_base + c * 16);
+    if (c + 1 < c1) {
+      tmem_ld_wait();
+      if (c + 2 < c1) {
+        tmem_ld_x16(t_row + (c + 2) * 16, r0);
+        if (has_res && n_base + (c + 2) * 16 < N) load_resid16(epi, out_row, n_base + (c + 2) * 16, rr0);
+      }
+      if (row_ok && n_base + (c + 1) * 16 < N)
+        epilogue_store16(r1, epi, bias_s + (c + 1) * 16, rr1, m, out_row, n_base + (c + 1) * 16);
+    }
   }
 }
 
@@ -291,8 +314,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         out_row = (long long)(m / epi.row_period) * epi.remap_stride + epi.remap_offset +
                   (m % epi.row_period);
       const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-      if (half == 0) epilogue_chunks<0, NCH0>(t_row, epi, bias_s, m, out_row, row_ok, n_base, N);
-      else           epilogue_chunks<NCH0, NCH>(t_row, epi, bias_s, m, out_row, row_ok, n_base, N);
+      epilogue_chunks(t_row, epi, bias_s, m, out_row, row_ok, n_base, N, half == 0 ? 0 : NCH0,
+                      half == 0 ? NCH0 : NCH);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
