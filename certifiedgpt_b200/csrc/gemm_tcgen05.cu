@@ -26,12 +26,16 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARPS = 8;
 
-template <int BN>
+// CTAS = 1: one CTA owns a 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, cta_group::2) owns a
+// 256 x BN tile; each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), so shared
+// memory write (TMA) and read (UMMA) traffic per SM drops by a third and L2->SM traffic by a third.
+template <int BN, int CTAS>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = BN / CTAS;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 176 ? 5 : 6);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/;
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
   static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
@@ -190,12 +194,12 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams&
   }
 }
 
-template <int BN>
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
                          EpiParams epi) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -212,7 +216,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + BM - 1) / BM;
+  // a "tile" is (BM*CTAS) x BN; with CTAS = 2 both CTAs of the pair walk the same tile sequence
+  const int cta_rank = CTAS == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int worker = blockIdx.x / CTAS, num_workers = gridDim.x / CTAS;
+  const int m_tiles = (M + BM * CTAS - 1) / (BM * CTAS);
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
@@ -228,17 +235,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], EPI_WARPS);
+      mbar_init(&tmem_empty[i], EPI_WARPS * CTAS);   // both CTAs' epilogues release the leader's MMA
     }
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_2sm(tmem_ptr, 512); tmem_relinquish_2sm(); }
+    else           { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CTAS == 2) { __syncthreads(); cluster_sync_all(); } else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -247,26 +255,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int m_blk = (tile / n_tiles) * CTAS + cta_rank, n_blk = tile % n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (CTAS == 2) {
+            // the leader's barrier collects the bytes of BOTH CTAs' loads
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d_2sm(smem_b + stage * Cfg::B_BYTES, &tma_b, &full_bar[stage], kb * BK,
+                            n_blk * BN + cta_rank * Cfg::B_ROWS);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CTAS, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
@@ -278,12 +294,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in (addr >> 4) units
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (CTAS == 2) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else           umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          if (CTAS == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (CTAS == 2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -296,8 +313,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     constexpr int NCH0 = (NCH + 1) / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      const int m_blk = (tile / n_tiles) * CTAS + cta_rank, n_blk = tile % n_tiles;
       const int n_base = n_blk * BN;
       float* bias_s = bias_smem + acc * 256;
       if (epi.bias != nullptr && epi_tid < BN) {
@@ -318,16 +335,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                       half == 0 ? NCH0 : NCH);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tcgen05_fence_before();
+  __syncwarp();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // peer smem / barriers stay valid until both CTAs are done
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CTAS == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -369,21 +388,33 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
 static int g_num_sms = 0;
 static int g_gemm_launches = 0;
 
-template <int BN>
+template <int BN, int CTAS>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                        const EpiParams& epi, int max_ctas, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   static bool configured = false;
   if (!configured) {
-    CGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
+    CGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
-  CGPT_CHECK_CUDA(cudaGetLastError());
+  const int tiles = ((M + BM * CTAS - 1) / (BM * CTAS)) * ((N + BN - 1) / BN);
+  int workers = g_num_sms / CTAS;
+  if (max_ctas > 0 && workers > max_ctas / CTAS) workers = max_ctas / CTAS > 0 ? max_ctas / CTAS : 1;
+  if (tiles < workers) workers = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(workers * CTAS);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS>, ta, tb, M, N, K, epi));
   ++g_gemm_launches;
   return 0;
 }
@@ -425,14 +456,24 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   CGPT_REQUIRE(p.act != CGPT_ACT_SWIGLU || (!p.out_f32 && p.resid == nullptr && p.row_add == nullptr),
                "gemm: SwiGLU epilogue writes bf16 and takes no residual");
 
-  const int bn = force_bn > 0 ? force_bn : pick_bn(N);
+  // force_bn: low 12 bits = N tile (0 = auto); 0x1000 forces 1-CTA tiles, 0x2000 forces CTA pairs
+  int ctas = M > BM ? 2 : 1;
+  if (force_bn & 0x1000) ctas = 1;
+  if (force_bn & 0x2000) ctas = 2;
+  // measured on B200: CTA pairs are fastest with 256-wide tiles even when N (1408, 4224) leaves a
+  // masked tail; 1-CTA tiles prefer an exact divisor of N
+  int bn = (force_bn & 0xfff);
+  if (bn == 0) bn = ctas == 2 ? (N > 176 ? 256 : (N > 128 ? 176 : 128)) : pick_bn(N);
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, A, M, K, lda, BM)) return rc;
-  if (int rc = make_tmap(&tb, W, N, K, ldw, bn)) return rc;
-  switch (bn) {
-    case 256: return launch_gemm<256>(ta, tb, M, N, K, p, e->max_ctas, stream);
-    case 176: return launch_gemm<176>(ta, tb, M, N, K, p, e->max_ctas, stream);
-    case 128: return launch_gemm<128>(ta, tb, M, N, K, p, e->max_ctas, stream);
+  if (int rc = make_tmap(&tb, W, N, K, ldw, bn / ctas)) return rc;
+  switch (bn * 10 + ctas) {
+    case 2561: return launch_gemm<256, 1>(ta, tb, M, N, K, p, e->max_ctas, stream);
+    case 1761: return launch_gemm<176, 1>(ta, tb, M, N, K, p, e->max_ctas, stream);
+    case 1281: return launch_gemm<128, 1>(ta, tb, M, N, K, p, e->max_ctas, stream);
+    case 2562: return launch_gemm<256, 2>(ta, tb, M, N, K, p, e->max_ctas, stream);
+    case 1762: return launch_gemm<176, 2>(ta, tb, M, N, K, p, e->max_ctas, stream);
+    case 1282: return launch_gemm<128, 2>(ta, tb, M, N, K, p, e->max_ctas, stream);
     default: CGPT_REQUIRE(false, "gemm: unsupported N tile %d", bn);
   }
   return 0;

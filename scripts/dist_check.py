@@ -1,0 +1,51 @@
+"""Multi-GPU check (run under torchrun, one rank per GPU): the counts of a Smooth.certify whose
+draws are sharded over W ranks equal the single-GPU counts bit for bit (noise keyed by global
+sample index; only the int64 count vector is all-reduced over NCCL)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from certifiedgpt_b200.config import ModelConfig
+from certifiedgpt_b200.engine import MiniGPT4Engine
+from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+from certifiedgpt_b200.weights import random_state_dict, round_to_bf16
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    full = "--full" in sys.argv
+    cfg = ModelConfig.full(224) if full else ModelConfig.tiny()
+    sd = random_state_dict(cfg, seed=0, device=dev) if full else round_to_bf16(random_state_dict(cfg, seed=3))
+    V = cfg.llm.vocab
+    g = torch.Generator().manual_seed(7)
+    prefix = [1] + torch.randint(3, V, (6,), generator=g).tolist()
+    suffix = torch.randint(3, V, (12,), generator=g).tolist()
+    table = [((t,), t % 9) for t in range(3, V)]
+    eng = MiniGPT4Engine(cfg, sd, prefix, suffix, table, 10, max_new_tokens=1, device=dev)
+    S = cfg.vit.img_size
+    x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(1000)).to(dev)
+    n0, n = (16, 96) if full else (100, 1000)
+    sharded = Smooth(eng, 10, 0.25, seed=42, process_group=True)
+    res = sharded.certify(x, n0, n, 0.001, 64)
+    sel, est = sharded.last_counts_selection.clone(), sharded.last_counts_estimation.clone()
+    single = Smooth(eng, 10, 0.25, seed=42)           # every rank recomputes the whole range alone
+    res1 = single.certify(x, n0, n, 0.001, 64)
+    ok = (res == res1 and torch.equal(sel, single.last_counts_selection)
+          and torch.equal(est, single.last_counts_estimation) and int(est.sum()) == n)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"world={world} sharded={res} single={res1} counts_est={est.tolist()} "
+              f"{'DIST_OK' if flag.item() == 1 else 'DIST_MISMATCH'}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

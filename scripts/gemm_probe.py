@@ -69,7 +69,18 @@ def perf(M, N, K, bn=0, iters=20, **kw):
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
     oks = []
-    oks.append(case(128, 128, 64, 128))
+    C1, C2 = 0x1000, 0x2000
+    print("--- CTA-pair (cta_group::2) kernels", flush=True)
+    oks.append(case(256, 128, 64, 128 | C2))
+    oks.append(case(256, 256, 128, 256 | C2))
+    oks.append(case(256, 176, 256, 176 | C2))
+    oks.append(case(300, 1408, 592, C2))
+    oks.append(case(257 * 3, 4224, 1408, C2, bias=True))
+    oks.append(case(100, 256, 128, C2))
+    oks.append(case(20000, 6144, 1408, C2, bias=True, act=1))
+    oks.append(case(5000, 1408, 6144, C2, bias=True, resid="f32", f32out=True))
+    print("--- 1-CTA kernels", flush=True)
+    oks.append(case(128, 128, 64, 128 | C1))
     oks.append(case(128, 128, 256, 128))
     oks.append(case(128, 256, 128, 256))
     oks.append(case(128, 176, 128, 176))
@@ -85,13 +96,14 @@ if __name__ == "__main__":
     print("ALL_OK" if all(oks) else "SOME_BAD", flush=True)
     if "--perf" in sys.argv and oks[0]:
         B = 256
-        perf(B * 257, 4224, 1408)
-        perf(B * 257, 4224, 1408, bn=176)
-        perf(B * 257, 1408, 1408)
-        perf(B * 257, 1408, 1408, bn=128)
-        perf(B * 257, 1408, 1408, bn=256)
-        perf(B * 257, 6144, 1408, act=1)
-        perf(B * 257, 1408, 6144)
-        perf(8192, 8192, 8192)
-        perf(B * 72, 12288, 4096)
-        perf(B * 72, 22016, 4096, act=2)
+        for flag in (0x1000, 0x2000):
+            print("--- perf with", "1-CTA" if flag == 0x1000 else "CTA pairs", flush=True)
+            perf(B * 257, 4224, 1408, bn=flag)
+            perf(B * 257, 4224, 1408, bn=256 | flag)
+            perf(B * 257, 1408, 1408, bn=flag)
+            perf(B * 257, 1408, 1408, bn=256 | flag)
+            perf(B * 257, 6144, 1408, bn=flag, act=1)
+            perf(B * 257, 1408, 6144, bn=flag)
+            perf(8192, 8192, 8192, bn=flag)
+            perf(B * 72, 12288, 4096, bn=flag)
+            perf(B * 72, 22016, 4096, bn=flag, act=2)
