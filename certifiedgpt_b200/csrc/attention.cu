@@ -49,6 +49,12 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int FA_BM = 64, FA_BN = 64, FA_THREADS = 128;
 
 template <int HD>
@@ -133,10 +139,13 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(AttnParams p) {
       float s[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+      // keys valid in this tile (T=257 leaves ONE key in the 5th tile: skip its other MMAs)
+      const int nvalid = min(FA_BN, p.Tk - j * FA_BN);
 #pragma unroll
       for (int ks = 0; ks < KSTEPS; ++ks) {
 #pragma unroll
         for (int np = 0; np < 4; ++np) {  // pairs of 8-wide key tiles
+          if (np * 16 >= nvalid) continue;
           uint32_t b0, b1, b2, b3;
           const uint32_t addr = kt + ((np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8) * 2;
           ldmatrix_x4(addr, b0, b1, b2, b3);
@@ -166,7 +175,7 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(AttnParams p) {
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
         const float m_new = fmaxf(m_run[r], mx[r]);
         m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
-        corr[r] = exp2f(m_run[r] - m_use[r]);
+        corr[r] = fast_exp2(m_run[r] - m_use[r]);
         m_run[r] = m_new;
         l_run[r] *= corr[r];
       }
@@ -175,7 +184,7 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(AttnParams p) {
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float pv = exp2f(s[nt][e] - m_use[e >> 1]);
+          const float pv = fast_exp2(s[nt][e] - m_use[e >> 1]);
           s[nt][e] = pv;
           rs[e >> 1] += pv;
         }
@@ -190,6 +199,7 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(AttnParams p) {
       // O += P V
 #pragma unroll
       for (int kk = 0; kk < FA_BN / 16; ++kk) {
+        if (kk * 16 >= nvalid) continue;
         uint32_t pa[4];
         pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
         pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);

@@ -194,6 +194,21 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams&
   }
 }
 
+// Tile rasterisation: bands of GROUP_M m-tiles, m fastest inside a band.  The CTAs running at any
+// moment then share ~GROUP_M A tiles and only ~(#CTAs / GROUP_M) weight tiles, so the working set
+// stays inside the 126 MB L2 even for the 180 MB Llama gate/up weight (n-fastest order re-read the
+// whole weight from HBM once per m-tile: 35 GB of DRAM reads for 0.77 GB of operands, ncu r01).
+constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& m, int& n) {
+  const int band = GROUP_M * n_tiles;
+  const int g = tile / band;
+  const int first_m = g * GROUP_M;
+  const int gm = min(GROUP_M, m_tiles - first_m);
+  const int r = tile - g * band;
+  m = first_m + r % gm;
+  n = r / gm;
+}
+
 template <int BN, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
@@ -256,7 +271,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        const int m_blk = (tile / n_tiles) * CTAS + cta_rank, n_blk = tile % n_tiles;
+        int m_blk, n_blk;
+        tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
+        m_blk = m_blk * CTAS + cta_rank;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (CTAS == 2) {
@@ -314,7 +331,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
-      const int m_blk = (tile / n_tiles) * CTAS + cta_rank, n_blk = tile % n_tiles;
+      int m_blk, n_blk;
+      tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
+      m_blk = m_blk * CTAS + cta_rank;
       const int n_base = n_blk * BN;
       float* bias_s = bias_smem + acc * 256;
       if (epi.bias != nullptr && epi_tid < BN) {
