@@ -102,3 +102,48 @@ def round_to_bf16(sd):
         else:
             out[k] = t.clone()
     return out
+
+
+# ------------------------------------------------------------------------------- weight import
+def interpolate_pos_embed(pos_embed, new_tokens, num_extra_tokens=1):
+    """Bicubic resize of the ViT position grid to another image size (eva_vit.py:383-404);
+    the class token's embedding is kept.  pos_embed: [1, 1+g*g, D] -> [1, new_tokens, D]."""
+    pos_embed = pos_embed.float()
+    D = pos_embed.shape[-1]
+    orig = int((pos_embed.shape[-2] - num_extra_tokens) ** 0.5)
+    new = int((new_tokens - num_extra_tokens) ** 0.5)
+    if orig == new:
+        return pos_embed
+    extra = pos_embed[:, :num_extra_tokens]
+    grid = pos_embed[:, num_extra_tokens:].reshape(-1, orig, orig, D).permute(0, 3, 1, 2)
+    grid = torch.nn.functional.interpolate(grid, size=(new, new), mode="bicubic", align_corners=False)
+    grid = grid.permute(0, 2, 3, 1).flatten(1, 2)
+    return torch.cat((extra, grid), dim=1)
+
+
+def import_state_dicts(cfg, vit_sd=None, qformer_sd=None, minigpt4_sd=None, llama_sd=None):
+    """Assemble an engine state dict from the checkpoints the reference loads:
+      vit_sd       eva_vit_g.pth keys (eva_vit.py:444-454) -> `visual_encoder.*`, pos-embed resized
+      qformer_sd   BLIP-2 checkpoint `model` dict (base_model.py:249-267): `Qformer.*`, `query_tokens`,
+                   `ln_vision.*`
+      minigpt4_sd  MiniGPT-4 checkpoint `model_state_dict` (minigpt4.py:193-197): `llama_proj.*` and
+                   any fine-tuned overrides
+      llama_sd     HF LlamaForCausalLM state dict -> `llama_model.*`
+    Later sources override earlier ones, as successive load_state_dict(strict=False) calls do."""
+    out = {}
+    if vit_sd is not None:
+        for k, v in vit_sd.items():
+            out["visual_encoder." + k] = v
+        pe = "visual_encoder.pos_embed"
+        if pe in out:
+            out[pe] = interpolate_pos_embed(out[pe], cfg.vit.tokens)
+    for src in (qformer_sd, minigpt4_sd):
+        if src is not None:
+            for k, v in src.items():
+                if k.startswith(("Qformer.", "query_tokens", "ln_vision.", "llama_proj.", "visual_encoder.",
+                                 "llama_model.")):
+                    out[k] = v
+    if llama_sd is not None:
+        for k, v in llama_sd.items():
+            out["llama_model." + k] = v
+    return out

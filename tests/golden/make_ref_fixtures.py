@@ -137,5 +137,21 @@ def main():
     torch.save(out_qf, os.path.join(HERE, "ref_qformer.pt"))
 
 
+def make_pos_interp_fixture():
+    """ref_pos_interp.pt: the reference's interpolate_pos_embed (eva_vit.py:383-404) 4x4 -> 8x8."""
+    _install_shims()
+    eva = _load("ref_eva_vit", os.path.join(REF, "eva_vit.py"))
+
+    class FakeModel:
+        class patch_embed:
+            num_patches = 64
+        pos_embed = torch.zeros(1, 65, 16)
+    inp = torch.randn(1, 17, 16, generator=torch.Generator().manual_seed(12))
+    ck = {"pos_embed": inp.clone()}
+    eva.interpolate_pos_embed(FakeModel, ck)
+    torch.save({"in": inp, "out": ck["pos_embed"]}, os.path.join(HERE, "ref_pos_interp.pt"))
+
+
 if __name__ == "__main__":
     main()
+    make_pos_interp_fixture()

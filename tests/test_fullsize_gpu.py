@@ -87,3 +87,44 @@ def test_full_size_certify_deterministic_and_consistent(full_engine):
     from oracle import smoothing_oracle as so
     ref = so.certify_tail(sel1.cpu().numpy(), est1.cpu().numpy(), 64, 0.001, 0.25)
     assert r1[0] == ref[0] and r1[1] == pytest.approx(ref[1], rel=1e-9)
+
+
+def test_448px_path_matches_oracle():
+    """Every shipped reference config uses image_size 448 (1025 ViT tokens)."""
+    from certifiedgpt_b200.engine import MiniGPT4Engine
+    cfg = ModelConfig.tiny()
+    cfg.vit.img_size = 448
+    assert cfg.vit.tokens == 1025
+    sd = round_to_bf16(random_state_dict(cfg, seed=13))
+    table = [((t,), t % 5) for t in range(3, cfg.llm.vocab)]
+    eng = MiniGPT4Engine(cfg, sd, (1, 4), (6, 7, 8), table, 6, max_new_tokens=1)
+    images = torch.randn(2, 3, 448, 448, generator=torch.Generator().manual_seed(5))
+    got, ref = {}, {}
+    eng.forward_images(images.cuda(), collect=got)
+    with torch.no_grad():
+        mo.encode_img(sd, cfg, images, collect=ref)
+    for k in ("embed", "block1", "image_embeds", "layer1"):
+        assert _rel(got[k], ref[k]) < 2e-2, k
+
+
+def test_full_width_llm_matches_oracle():
+    """Llama-2-7B widths (4096 / 32 heads x 128 / 11008 / vocab 32000), 2 layers: logits within bf16
+    tolerance and greedy ids exact where the oracle margin is safe."""
+    from certifiedgpt_b200.engine import MiniGPT4Engine
+    cfg = ModelConfig.tiny()
+    cfg.llm = LlmConfig(layers=2)
+    sd = round_to_bf16(random_state_dict(cfg, seed=17))
+    g = torch.Generator().manual_seed(7)
+    prefix = [1] + torch.randint(3, 32000, (6,), generator=g).tolist()
+    suffix = torch.randint(3, 32000, (9,), generator=g).tolist()
+    table = [((t,), t % 9) for t in range(3, 32000)]
+    eng = MiniGPT4Engine(cfg, sd, prefix, suffix, table, 10, max_new_tokens=3)
+    orc = mo.MiniGPT4ClassifierOracle(sd, cfg, prefix, suffix, table, 10, max_new_tokens=3)
+    images = torch.randn(4, 3, cfg.vit.img_size, cfg.vit.img_size, generator=torch.Generator().manual_seed(6))
+    got = {}
+    labels = eng.forward_images(images.cuda(), collect=got)
+    orc(images)
+    assert _rel(got["first_logits"], orc.last["first_logits"]) < 2e-2
+    safe = (orc.last["margins"] > 1e-2).all(dim=1)
+    assert torch.equal(got["ids"].cpu().long()[safe], orc.last["ids"][safe])
+    assert torch.equal(labels.cpu().long()[safe], orc.last["labels"][safe])

@@ -98,3 +98,15 @@ def test_classifier_oracle_end_to_end_tiny():
     out = clf(x)
     assert out.shape == (4, 8) and torch.equal(out.sum(1), torch.ones(4))
     assert clf.last["ids"].shape == (4, 1)
+
+
+def test_pos_embed_interpolation_matches_reference():
+    from certifiedgpt_b200.weights import import_state_dicts, interpolate_pos_embed
+    ref = torch.load(os.path.join(GOLD, "ref_pos_interp.pt"))
+    assert torch.equal(interpolate_pos_embed(ref["in"], 65), ref["out"])
+    assert interpolate_pos_embed(ref["in"], 17) is not None and interpolate_pos_embed(ref["in"], 17).shape == (1, 17, 16)
+    # import path: eva_vit_g.pth-style keys are prefixed and the grid is resized for the configured image size
+    cfg = ModelConfig.tiny()
+    cfg.vit.img_size = 112                       # 8x8 patches + cls = 65 tokens
+    sd = import_state_dicts(cfg, vit_sd={"pos_embed": ref["in"], "cls_token": torch.zeros(1, 1, 16)})
+    assert torch.equal(sd["visual_encoder.pos_embed"], ref["out"]) and "visual_encoder.cls_token" in sd
