@@ -55,16 +55,16 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-constexpr int FA_BM = 64, FA_BN = 64, FA_THREADS = 128;
+constexpr int FA_BN = 64;   // key/value tile rows; the query tile is 16 rows per warp (NW warps)
 
-template <int HD>
+template <int HD, int ROWS, int THREADS>
 __device__ __forceinline__ void load_rows_tile(uint32_t smem_tile, const __nv_bfloat16* base, long long ld,
                                                int row0, int nrows_valid, int head_dim,
                                                const __nv_bfloat16* pbase, long long pld, int P) {
-  // 64 rows x HD cols, 16-byte chunks; rows >= nrows_valid and cols >= head_dim are zero-filled
+  // ROWS rows x HD cols, 16-byte chunks; rows >= nrows_valid and cols >= head_dim are zero-filled
   constexpr int CH = HD / 8;
   constexpr int LDS = HD + 8;
-  for (int i = threadIdx.x; i < FA_BN * CH; i += FA_THREADS) {
+  for (int i = threadIdx.x; i < ROWS * CH; i += THREADS) {
     const int r = i / CH, c = i - r * CH;
     const int row = row0 + r;
     const bool valid = row < nrows_valid && c * 8 < head_dim;
@@ -74,8 +74,10 @@ __device__ __forceinline__ void load_rows_tile(uint32_t smem_tile, const __nv_bf
   }
 }
 
-template <int HD>
-__global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(AttnParams p) {
+template <int HD, int NW>
+__global__ void __launch_bounds__(NW * 32) flash_attn_kernel(AttnParams p) {
+  constexpr int FA_BM = 16 * NW;
+  constexpr int FA_THREADS = 32 * NW;
   constexpr int LDS = HD + 8;
   constexpr int KSTEPS = HD / 16;
   constexpr int DTILES = HD / 8;
@@ -101,9 +103,9 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(AttnParams p) {
     n_tiles = min(n_tiles, (last_q + offs) / FA_BN + 1);
   }
 
-  load_rows_tile<HD>(sQ, qbase, p.ldq, q0, p.Tq, p.head_dim, nullptr, 0, 0);
-  load_rows_tile<HD>(sK, kbase, p.ldk, 0, p.Tk, p.head_dim, kpbase, p.ldkp, p.P);
-  load_rows_tile<HD>(sV, vbase, p.ldv, 0, p.Tk, p.head_dim, vpbase, p.ldvp, p.P);
+  load_rows_tile<HD, FA_BM, FA_THREADS>(sQ, qbase, p.ldq, q0, p.Tq, p.head_dim, nullptr, 0, 0);
+  load_rows_tile<HD, FA_BN, FA_THREADS>(sK, kbase, p.ldk, 0, p.Tk, p.head_dim, kpbase, p.ldkp, p.P);
+  load_rows_tile<HD, FA_BN, FA_THREADS>(sV, vbase, p.ldv, 0, p.Tk, p.head_dim, vpbase, p.ldvp, p.P);
   cp_async_commit();
 
   uint32_t qf[KSTEPS][4];
@@ -116,9 +118,9 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(AttnParams p) {
   for (int j = 0; j < n_tiles; ++j) {
     const int buf = j & 1;
     if (j + 1 < n_tiles) {
-      load_rows_tile<HD>(sK + (buf ^ 1) * FA_BN * LDS * 2, kbase, p.ldk, (j + 1) * FA_BN, p.Tk, p.head_dim,
+      load_rows_tile<HD, FA_BN, FA_THREADS>(sK + (buf ^ 1) * FA_BN * LDS * 2, kbase, p.ldk, (j + 1) * FA_BN, p.Tk, p.head_dim,
                          kpbase, p.ldkp, p.P);
-      load_rows_tile<HD>(sV + (buf ^ 1) * FA_BN * LDS * 2, vbase, p.ldv, (j + 1) * FA_BN, p.Tk, p.head_dim,
+      load_rows_tile<HD, FA_BN, FA_THREADS>(sV + (buf ^ 1) * FA_BN * LDS * 2, vbase, p.ldv, (j + 1) * FA_BN, p.Tk, p.head_dim,
                          vpbase, p.ldvp, p.P);
       cp_async_commit();
       cp_async_wait<1>();
@@ -153,29 +155,38 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(AttnParams p) {
           mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
         }
       }
-      // mask + online softmax (rows g and g+8 of this warp's 16)
+      // online softmax on RAW scores (rows g and g+8 of this warp's 16); the softmax scale is folded
+      // into the exp2 argument (one FFMA per element).  Masking code only runs on tiles that need it.
       const int qrow0 = q0 + warp * 16 + g;
+      const bool need_mask = (j * FA_BN + FA_BN > p.Tk) ||
+                             (p.causal && (j * FA_BN + FA_BN - 1 > q0 + warp * 16 + offs));
+      if (need_mask) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = j * FA_BN + nt * 8 + 2 * t + (e & 1);
+            const int qrow = qrow0 + (e >> 1) * 8;
+            const bool ok = col < p.Tk && (!p.causal || col <= qrow + offs);
+            if (!ok) s[nt][e] = -INFINITY;
+          }
+        }
+      }
       float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = j * FA_BN + nt * 8 + 2 * t + (e & 1);
-          const int qrow = qrow0 + (e >> 1) * 8;
-          const bool ok = col < p.Tk && (!p.causal || col <= qrow + offs);
-          const float val = ok ? s[nt][e] * p.scale_log2e : -INFINITY;
-          s[nt][e] = val;
-          mx[e >> 1] = fmaxf(mx[e >> 1], val);
-        }
+        mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
       }
-      float corr[2], m_use[2];
+      float corr[2], neg_ms[2];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
         const float m_new = fmaxf(m_run[r], mx[r]);
-        m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
-        corr[r] = fast_exp2(m_run[r] - m_use[r]);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        corr[r] = fast_exp2((m_run[r] - m_use) * p.scale_log2e);
+        neg_ms[r] = -m_use * p.scale_log2e;
         m_run[r] = m_new;
         l_run[r] *= corr[r];
       }
@@ -184,17 +195,19 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(AttnParams p) {
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float pv = fast_exp2(s[nt][e] - m_use[e >> 1]);
+          const float pv = fast_exp2(fmaf(s[nt][e], p.scale_log2e, neg_ms[e >> 1]));
           s[nt][e] = pv;
           rs[e >> 1] += pv;
         }
       }
       l_run[0] += rs[0];
       l_run[1] += rs[1];
+      if (corr[0] != 1.f || corr[1] != 1.f) {   // (per-thread; skipping is exact when the max did not move)
 #pragma unroll
-      for (int dt = 0; dt < DTILES; ++dt) {
-        o_acc[dt][0] *= corr[0]; o_acc[dt][1] *= corr[0];
-        o_acc[dt][2] *= corr[1]; o_acc[dt][3] *= corr[1];
+        for (int dt = 0; dt < DTILES; ++dt) {
+          o_acc[dt][0] *= corr[0]; o_acc[dt][1] *= corr[0];
+          o_acc[dt][2] *= corr[1]; o_acc[dt][3] *= corr[1];
+        }
       }
       // O += P V
 #pragma unroll
@@ -306,19 +319,32 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(AttnParams p) {
 }
 
 // ---------------------------------------------------------------- host
-template <int HD>
-static int launch_flash(const AttnParams& p, int B, int H, cudaStream_t stream) {
-  constexpr int smem = 5 * FA_BM * (HD + 8) * 2;
+template <int HD, int NW>
+static int launch_flash_nw(const AttnParams& p, int B, int H, cudaStream_t stream) {
+  constexpr int BMQ = 16 * NW;
+  constexpr int smem = (BMQ + 4 * FA_BN) * (HD + 8) * 2;
   static bool configured = false;
   if (!configured) {
-    CGPT_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CGPT_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((p.Tq + FA_BM - 1) / FA_BM, H, B);
-  flash_attn_kernel<HD><<<grid, FA_THREADS, smem, stream>>>(p);
+  dim3 grid((p.Tq + BMQ - 1) / BMQ, H, B);
+  flash_attn_kernel<HD, NW><<<grid, NW * 32, smem, stream>>>(p);
   CGPT_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+// query-tile height: 2 warps for <= 32 query rows (Q-Former), 5 warps when 64 < Tq <= 80 (the 72-row
+// Llama prefill fits ONE tile instead of 64 + 8); otherwise 4 or 6 warps, whichever pads Tq less
+// (T=257: 3 tiles of 96 = 288 rows instead of 5 tiles of 64 = 320, and 3 instead of 5 K/V sweeps)
+template <int HD>
+static int launch_flash(const AttnParams& p, int B, int H, cudaStream_t stream) {
+  if (p.Tq <= 32) return launch_flash_nw<HD, 2>(p, B, H, stream);
+  if (p.Tq > 64 && p.Tq <= 80) return launch_flash_nw<HD, 5>(p, B, H, stream);
+  const int pad4 = (p.Tq + 63) / 64 * 64, pad6 = (p.Tq + 95) / 96 * 96;
+  if (pad6 < pad4) return launch_flash_nw<HD, 6>(p, B, H, stream);
+  return launch_flash_nw<HD, 4>(p, B, H, stream);
 }
 
 int attention(const cgpt_attn_args* a, cudaStream_t stream) {
