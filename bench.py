@@ -283,6 +283,17 @@ def run_ours(args, cfg):
         a = by_shape.setdefault(k, [0.0, 0.0, 0])
         a[0] += t; a[1] += fl; a[2] += 1
     top = sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:6]
+    # DRAM traffic of the most expensive GEMM shape, from the committed ncu --set full capture
+    traffic, traffic_note = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
+        if top and top[0][0] in tr:
+            t0 = tr[top[0][0]]
+            traffic = t0["dram_read_bytes"] + t0["dram_write_bytes"]
+            traffic_note = (f"{top[0][0]} (top shape, M={t0['M']}): {traffic / 1e9:.2f} GB DRAM per launch vs "
+                            f"{t0['algorithmic_bytes'] / 1e9:.2f} GB algorithmic; {t0['capture']}")
+    except Exception:
+        pass
 
     if rank == 0:
         line = {
@@ -297,7 +308,7 @@ def run_ours(args, cfg):
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the timed steps)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
                          "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
                          "gemm_launches": len(prof),
                          "top_shapes": {k: {"ms": round(v[0], 3), "tflops": round(v[1] / (v[0] / 1e3) / 1e12, 1), "launches": v[2]}
