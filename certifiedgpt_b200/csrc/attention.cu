@@ -257,65 +257,99 @@ __global__ void __launch_bounds__(NW * 32) flash_attn_kernel(AttnParams p) {
 }
 
 // ---------------------------------------------------------------- single-token decode
-// one warp per (batch, head); lanes own key positions for QK^T, then 4 dims each for PV
+// One warp per (batch, head).  8 lanes cooperate on one K/V row (a 256-byte row of a 128-wide head is
+// read as 8 x 32 B, fully coalesced), 4 rows per warp iteration; scores go through shared memory for the
+// softmax, then the same mapping accumulates P.V.  HBM-bound: KV bytes per (batch, head) = 2*Tk*HD*2.
+template <int N>
+__device__ __forceinline__ void load_bf16_vec(const __nv_bfloat16* src, float* v) {
+  if constexpr (N == 16) {
+    const uint4 a = *reinterpret_cast<const uint4*>(src);
+    const uint4 b = *reinterpret_cast<const uint4*>(src + 8);
+    v[0] = bf16_lo(a.x); v[1] = bf16_hi(a.x); v[2] = bf16_lo(a.y); v[3] = bf16_hi(a.y);
+    v[4] = bf16_lo(a.z); v[5] = bf16_hi(a.z); v[6] = bf16_lo(a.w); v[7] = bf16_hi(a.w);
+    v[8] = bf16_lo(b.x); v[9] = bf16_hi(b.x); v[10] = bf16_lo(b.y); v[11] = bf16_hi(b.y);
+    v[12] = bf16_lo(b.z); v[13] = bf16_hi(b.z); v[14] = bf16_lo(b.w); v[15] = bf16_hi(b.w);
+  } else if constexpr (N == 8) {
+    const uint4 a = *reinterpret_cast<const uint4*>(src);
+    v[0] = bf16_lo(a.x); v[1] = bf16_hi(a.x); v[2] = bf16_lo(a.y); v[3] = bf16_hi(a.y);
+    v[4] = bf16_lo(a.z); v[5] = bf16_hi(a.z); v[6] = bf16_lo(a.w); v[7] = bf16_hi(a.w);
+  } else {
+    const uint2 a = *reinterpret_cast<const uint2*>(src);
+    v[0] = bf16_lo(a.x); v[1] = bf16_hi(a.x); v[2] = bf16_lo(a.y); v[3] = bf16_hi(a.y);
+  }
+}
+
 template <int HD>
 __global__ void __launch_bounds__(128) decode_attn_kernel(AttnParams p) {
   constexpr int MAX_CTX = 1024;
-  __shared__ float s_q[4][HD];
+  constexpr int DPL = HD / 8;  // dims per lane: 8 lanes span one head row
   __shared__ float s_p[4][MAX_CTX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane & 7, grp = lane >> 3;
   const int h = blockIdx.x * 4 + warp, b = blockIdx.y;
-  const __nv_bfloat16* q = p.q + static_cast<long long>(b) * p.q_rows_per_batch * p.ldq + h * HD;
-  const __nv_bfloat16* kbase = p.k + static_cast<long long>(b) * p.kv_rows_per_batch * p.ldk + h * HD;
-  const __nv_bfloat16* vbase = p.v + static_cast<long long>(b) * p.kv_rows_per_batch * p.ldv + h * HD;
-  for (int d = lane; d < HD; d += 32) s_q[warp][d] = __bfloat162float(q[d]);
-  __syncwarp();
-  float mx = -INFINITY;
-  for (int pos = lane; pos < p.Tk; pos += 32) {
-    const __nv_bfloat16* kr = pos < p.P ? p.kp + static_cast<long long>(pos) * p.ldkp + h * HD
-                                        : kbase + static_cast<long long>(pos - p.P) * p.ldk;
-    float acc = 0.f;
+  const __nv_bfloat16* q = p.q + static_cast<long long>(b) * p.q_rows_per_batch * p.ldq + h * HD + sub * DPL;
+  const __nv_bfloat16* kbase = p.k + static_cast<long long>(b) * p.kv_rows_per_batch * p.ldk + h * HD + sub * DPL;
+  const __nv_bfloat16* vbase = p.v + static_cast<long long>(b) * p.kv_rows_per_batch * p.ldv + h * HD + sub * DPL;
+  const __nv_bfloat16* kpb = p.kp ? p.kp + h * HD + sub * DPL : nullptr;
+  const __nv_bfloat16* vpb = p.vp ? p.vp + h * HD + sub * DPL : nullptr;
+  float qv[DPL];
+  load_bf16_vec<DPL>(q, qv);
 #pragma unroll
-    for (int c = 0; c < HD / 8; ++c) {
-      const uint4 kv = *reinterpret_cast<const uint4*>(kr + c * 8);
-      const float* qq = &s_q[warp][c * 8];
-      acc += bf16_lo(kv.x) * qq[0] + bf16_hi(kv.x) * qq[1] + bf16_lo(kv.y) * qq[2] + bf16_hi(kv.y) * qq[3] +
-             bf16_lo(kv.z) * qq[4] + bf16_hi(kv.z) * qq[5] + bf16_lo(kv.w) * qq[6] + bf16_hi(kv.w) * qq[7];
+  for (int i = 0; i < DPL; ++i) qv[i] *= p.scale_log2e;
+  float mx = -INFINITY;
+  for (int pos0 = 0; pos0 < p.Tk; pos0 += 4) {
+    const int pos = pos0 + grp;
+    float acc = 0.f;
+    if (pos < p.Tk) {
+      const __nv_bfloat16* kr = pos < p.P ? kpb + static_cast<long long>(pos) * p.ldkp
+                                          : kbase + static_cast<long long>(pos - p.P) * p.ldk;
+      float kv[DPL];
+      load_bf16_vec<DPL>(kr, kv);
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) acc = fmaf(kv[i], qv[i], acc);
     }
-    acc *= p.scale_log2e;
-    s_p[warp][pos] = acc;
-    mx = fmaxf(mx, acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (pos < p.Tk) {
+      if (sub == 0) s_p[warp][pos] = acc;
+      mx = fmaxf(mx, acc);
+    }
   }
   mx = warp_max(mx);
+  __syncwarp();
   float sum = 0.f;
   for (int pos = lane; pos < p.Tk; pos += 32) {
-    const float e = exp2f(s_p[warp][pos] - mx);
+    const float e = fast_exp2(s_p[warp][pos] - mx);
     s_p[warp][pos] = e;
     sum += e;
   }
   sum = warp_sum(sum);
   __syncwarp();
-  const float inv = 1.f / sum;
-  constexpr int DPL = HD / 32;  // dims per lane
   float acc[DPL];
 #pragma unroll
   for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
-  for (int pos = 0; pos < p.Tk; ++pos) {
-    const __nv_bfloat16* vr = pos < p.P ? p.vp + static_cast<long long>(pos) * p.ldvp + h * HD
+  for (int pos = grp; pos < p.Tk; pos += 4) {
+    const __nv_bfloat16* vr = pos < p.P ? vpb + static_cast<long long>(pos) * p.ldvp
                                         : vbase + static_cast<long long>(pos - p.P) * p.ldv;
     const float pr = s_p[warp][pos];
-    if (DPL == 4) {
-      const uint2 vv = *reinterpret_cast<const uint2*>(vr + lane * 4);
-      acc[0] += pr * bf16_lo(vv.x); acc[1] += pr * bf16_hi(vv.x);
-      acc[2] += pr * bf16_lo(vv.y); acc[3] += pr * bf16_hi(vv.y);
-    } else {
+    float vv[DPL];
+    load_bf16_vec<DPL>(vr, vv);
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) acc[i] += pr * __bfloat162float(vr[lane * DPL + i]);
-    }
+    for (int i = 0; i < DPL; ++i) acc[i] = fmaf(pr, vv[i], acc[i]);
   }
-  __nv_bfloat16* o = p.o + static_cast<long long>(b) * p.q_rows_per_batch * p.ldo + h * HD + lane * DPL;
+  const float inv = 1.f / sum;
 #pragma unroll
-  for (int i = 0; i < DPL; ++i) o[i] = __float2bfloat16(acc[i] * inv);
+  for (int i = 0; i < DPL; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    acc[i] *= inv;
+  }
+  if (grp == 0) {
+    __nv_bfloat16* o = p.o + static_cast<long long>(b) * p.q_rows_per_batch * p.ldo + h * HD + sub * DPL;
+#pragma unroll
+    for (int i = 0; i < DPL; i += 2) *reinterpret_cast<uint32_t*>(o + i) = pack_bf16x2(acc[i], acc[i + 1]);
+  }
 }
 
 // ---------------------------------------------------------------- host
