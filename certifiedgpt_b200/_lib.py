@@ -328,7 +328,7 @@ def norm_rows(x, gamma, beta, eps, out, *, rms=False, rows=None, gather=None):
 
 
 def attention(q, k, v, o, *, B, H, Tq, Tk, head_dim, scale, q_rows_per_batch=None,
-              kv_rows_per_batch=None, causal=False, kp=None, vp=None, P=0, decode=False):
+              kv_rows_per_batch=None, causal=False, kp=None, vp=None, P=0, decode=False, force_flash=False):
     """q/k/v/o are 2-D bf16 views whose column 0 is head 0 (e.g. slices of a fused QKV buffer)."""
     lib = load()
     a = AttnArgs()
@@ -340,7 +340,8 @@ def attention(q, k, v, o, *, B, H, Tq, Tk, head_dim, scale, q_rows_per_batch=Non
     a.P = P
     a.o = o.data_ptr(); a.ldo = o.stride(0)
     a.B, a.H, a.Tq, a.Tk, a.head_dim = B, H, Tq, Tk, head_dim
-    a.scale = float(scale); a.causal = 1 if causal else 0; a.decode_kernel = 1 if decode else 0
+    a.scale = float(scale); a.causal = 1 if causal else 0
+    a.decode_kernel = 1 if decode else (2 if force_flash else 0)
     check(lib.cgpt_attention(C.byref(a), stream_ptr()))
     return o
 

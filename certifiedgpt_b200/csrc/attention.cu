@@ -10,6 +10,7 @@
 // 224 px, so this legacy-tensor-path kernel is not on the roofline-critical path; the GEMMs are.
 // The K/V row index space is [shared prefix rows | per-batch rows]: rows < P are read from a
 // batch-invariant buffer (the "<s>[INST] <Img>" prompt prefix), the rest from this batch's rows.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ops.h"
 
@@ -391,6 +392,10 @@ int attention(const cgpt_attn_args* a, cudaStream_t stream) {
   CGPT_REQUIRE(a->P >= 0 && a->P <= a->Tk && (a->P == 0 || (a->kp && a->vp)), "attention: bad prefix");
   CGPT_REQUIRE(a->Tk - a->P <= a->kv_rows_per_batch && a->Tq <= a->q_rows_per_batch,
                "attention: rows per batch too small");
+  // tcgen05 one-shot kernel for the ViT / Llama-prefill shapes; mma.sync flash kernel otherwise
+  // (CGPT_ATTN_LEGACY=1 forces the flash kernel, used by the parity tests to cover both)
+  static const bool legacy = getenv("CGPT_ATTN_LEGACY") != nullptr;
+  if (!legacy && a->decode_kernel != 2 && attn_umma_supported(a)) return attention_umma(a, stream);
   AttnParams p;
   p.q = (const __nv_bfloat16*)a->q; p.ldq = a->ldq; p.q_rows_per_batch = a->q_rows_per_batch;
   p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v; p.ldk = a->ldk; p.ldv = a->ldv;
@@ -401,7 +406,7 @@ int attention(const cgpt_attn_args* a, cudaStream_t stream) {
   p.Tq = a->Tq; p.Tk = a->Tk; p.head_dim = a->head_dim;
   p.scale_log2e = a->scale * 1.4426950408889634f;
   p.causal = a->causal;
-  if (a->Tq == 1 && a->decode_kernel) {
+  if (a->Tq == 1 && a->decode_kernel == 1) {
     CGPT_REQUIRE(a->H % 4 == 0 && a->Tk <= 1024, "decode attention: H %% 4 == 0 and Tk <= 1024 required");
     dim3 grid(a->H / 4, a->B);
     if (a->head_dim == 128) decode_attn_kernel<128><<<grid, 128, 0, stream>>>(p);

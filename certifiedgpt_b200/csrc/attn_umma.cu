@@ -1,0 +1,400 @@
+// One-shot attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) for the two shapes that
+// dominate the non-GEMM time of the smoothing path:
+//   - EVA ViT self-attention, T = 257 = 1 cls + 256 patches, 16 heads x 88       (eva_vit.py:133-150)
+//   - Llama prefill over [prefix | image | question] rows, <= 256 keys, causal     (HF LlamaAttention)
+//
+// One CTA per (batch, head).  All keys fit one UMMA N (<= 256), so there is no online-softmax loop:
+//   TMA   : Q tile(s) [128 x hd], K [nk x hd], V [nk x hd] -> 128B-swizzled shared memory
+//   UMMA  : S = Q K^T (M=128, N=nk, K=hd in 16-steps)            -> TMEM, fp32
+//   warps : thread-per-row softmax straight out of TMEM (two passes: max, then exp/sum),
+//           unnormalised P as bf16 into shared memory (K-major, 128B swizzle) over the dead K/Q tiles
+//   UMMA  : O = P V  (M=128, N=128, K=nk; V is the MN-major B operand, read in place)  -> TMEM
+//   warps : O / rowsum -> bf16 -> global
+// ViT's 257th token would cost a whole extra 128-row tile and a 17th K-step; instead the cls KEY is
+// folded in on CUDA cores (one extra score per row, one rank-1 update of O) and the cls QUERY row is
+// computed by a spare warp, so every tensor-core tile is exactly 128 x 256.
+// hd = 88 is not a multiple of the UMMA K (16): Q's columns 88..95 are zeroed in shared memory, so
+// whatever K holds there (the next head's finite values) contributes nothing.
+#include "common.cuh"
+#include "ops.h"
+
+namespace cgpt {
+
+struct UmmaAttnParams {
+  const __nv_bfloat16* q; long long ldq; int q_rows_per_batch;
+  const __nv_bfloat16* k; const __nv_bfloat16* v; long long ldk, ldv; int kv_rows_per_batch;
+  __nv_bfloat16* o; long long ldo;
+  int H, head_dim, Tq, Tk, E, causal;  // Tq / Tk include the E extra (cls) row handled on CUDA cores
+  float scale_log2e;
+  int n_qtiles, nk_pad;                // 128-row query tiles; main keys padded to a multiple of 16
+  int tmem_cols, o_col1;               // TMEM allocation; column of O for q-tile 0 when it does not alias S
+  int q_bytes, k_region;               // smem carve-up
+};
+
+constexpr int UA_THREADS = 384;
+constexpr int SUB = 16384;  // one 128-row x 64-col bf16 sub-tile
+
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t addr) { return make_smem_desc_sw128(addr); }
+// MN-major operand, 128B swizzle: LBO = byte stride between 64-element MN atoms, SBO = 8-row K-group stride
+__device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+__device__ __forceinline__ float ua_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(UA_THREADS, 1)
+attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
+                 const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                 UmmaAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                       // n_qtiles x [sub0 | sub1]
+  uint8_t* sK = smem + p.q_bytes;           // [sub0 | sub1], sub stride nk_pad*128; later P of q-tile 0
+  uint8_t* sV = sK + p.k_region;            // [sub0 | sub1]
+  const int kv_sub = p.nk_pad * 128;
+  uint8_t* tail = sV + 2 * kv_sub;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* bar_qk = bars;       // TMA: Q + K landed
+  uint64_t* bar_v = bars + 1;    // TMA: V landed
+  uint64_t* bar_s = bars + 2;    // [2] S_qt in TMEM
+  uint64_t* bar_p = bars + 4;    // [2] P_qt in smem (128 arrivals)
+  uint64_t* bar_o = bars + 6;    // [2] O_qt in TMEM
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xk = reinterpret_cast<float*>(tail + 128);   // extra key   [128] fp32
+  float* xv = xk + 128;                               // extra value [128]
+  float* xq = xv + 128;                               // extra query [128], pre-scaled
+  float* xs = xq + 128;                               // extra-query scores [<= 288]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
+  const int hd = p.head_dim, E = p.E;
+  const int Tk_main = p.Tk - E, Tq_main = p.Tq - E;
+  const int hcol = h * hd;
+  const long long qrow_base = static_cast<long long>(b) * p.q_rows_per_batch;
+  const long long krow_base = static_cast<long long>(b) * p.kv_rows_per_batch;
+  const int ksteps_s = (hd + 15) / 16;
+  const int ksteps_o = p.nk_pad / 16;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q0); tma_prefetch_desc(&map_q1); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 128); mbar_init(&bar_o[i], 1); }
+    fence_barrier_init();
+    fence_proxy_async();
+    // ---- all loads of this (batch, head)
+    const int q1_cols = hd - 64;
+    const uint32_t q_tx = static_cast<uint32_t>(p.n_qtiles) * (64 * 128 * 2 + q1_cols * 128 * 2);
+    const uint32_t kv_tx = 2u * 64 * p.nk_pad * 2;
+    mbar_arrive_expect_tx(bar_qk, q_tx + kv_tx);
+    for (int qt = 0; qt < p.n_qtiles; ++qt) {
+      const int row = static_cast<int>(qrow_base) + E + qt * 128;
+      tma_load_2d(sQ + qt * 2 * SUB, &map_q0, bar_qk, hcol, row);
+      tma_load_2d(sQ + qt * 2 * SUB + SUB, &map_q1, bar_qk, hcol + 64, row);
+    }
+    tma_load_2d(sK, &map_k, bar_qk, hcol, static_cast<int>(krow_base) + E);
+    tma_load_2d(sK + kv_sub, &map_k, bar_qk, hcol + 64, static_cast<int>(krow_base) + E);
+    mbar_arrive_expect_tx(bar_v, kv_tx);
+    tma_load_2d(sV, &map_v, bar_v, hcol, static_cast<int>(krow_base) + E);
+    tma_load_2d(sV + kv_sub, &map_v, bar_v, hcol + 64, static_cast<int>(krow_base) + E);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp == 3 && E) {
+    // extra (cls) key / value / query of this head as fp32 in shared memory
+    const __nv_bfloat16* kx = p.k + krow_base * p.ldk + hcol;
+    const __nv_bfloat16* vx = p.v + krow_base * p.ldv + hcol;
+    const __nv_bfloat16* qx = p.q + qrow_base * p.ldq + hcol;
+    for (int d = lane; d < 128; d += 32) {
+      xk[d] = d < hd ? __bfloat162float(kx[d]) : 0.f;
+      xv[d] = d < hd ? __bfloat162float(vx[d]) : 0.f;
+      xq[d] = d < hd ? __bfloat162float(qx[d]) * p.scale_log2e : 0.f;
+    }
+  }
+  if (warp >= 4 && (hd & 15)) {
+    // zero Q's pad columns [hd, roundup16(hd)) of the second sub-tile: one 16-byte chunk per row.
+    // (disjoint from the bytes the TMA box writes; made visible to the tensor core by the proxy fence)
+    const int qt = (warp - 4) >> 2;
+    if (qt < p.n_qtiles) {
+      const int r = (warp & 3) * 32 + lane;
+      const int chunk = (hd - 64) >> 3;
+      uint8_t* dst = sQ + qt * 2 * SUB + SUB + r * 128 + ((chunk ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      fence_proxy_async();
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t o_col0 = p.n_qtiles == 2 ? 0u : static_cast<uint32_t>(p.o_col1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issue
+      const uint32_t idesc_s = make_idesc_bf16(128, p.nk_pad);
+      const uint32_t idesc_o = make_idesc_bf16(128, 128) | (1u << 16);   // B (= V) is MN-major
+      mbar_wait(bar_qk, 0);
+      tcgen05_fence_after();
+      for (int qt = 0; qt < p.n_qtiles; ++qt) {
+        const uint32_t d_tmem = tmem_base + qt * 256;
+        for (int ks = 0; ks < ksteps_s; ++ks) {
+          const uint64_t ad = make_desc_kmajor(smem_u32(sQ + qt * 2 * SUB + (ks >> 2) * SUB)) + 2 * (ks & 3);
+          const uint64_t bd = make_desc_kmajor(smem_u32(sK + (ks >> 2) * kv_sub)) + 2 * (ks & 3);
+          umma_bf16(d_tmem, ad, bd, idesc_s, ks != 0);
+        }
+        umma_commit(&bar_s[qt]);
+      }
+      mbar_wait(bar_v, 0);
+      for (int qt = 0; qt < p.n_qtiles; ++qt) {
+        mbar_wait(&bar_p[qt], 0);
+        tcgen05_fence_after();
+        const uint8_t* sP = qt == 0 ? sK : sQ;
+        const uint32_t d_tmem = tmem_base + (qt == 0 ? o_col0 : 256u);
+        for (int ks = 0; ks < ksteps_o; ++ks) {
+          const uint64_t ad = make_desc_kmajor(smem_u32(sP + (ks >> 2) * SUB)) + 2 * (ks & 3);
+          const uint64_t bd = make_desc_mnmajor(smem_u32(sV + ks * 16 * 128), static_cast<uint32_t>(kv_sub));
+          umma_bf16(d_tmem, ad, bd, idesc_o, ks != 0);
+        }
+        umma_commit(&bar_o[qt]);
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------------------------------------------------------- extra (cls) query row, CUDA cores
+    if (E) {
+      const __nv_bfloat16* kb = p.k + krow_base * p.ldk + hcol;
+      const __nv_bfloat16* vb = p.v + krow_base * p.ldv + hcol;
+      float mx = -INFINITY;
+      for (int j = lane; j < p.Tk; j += 32) {
+        const __nv_bfloat16* kr = kb + static_cast<long long>(j) * p.ldk;
+        float acc = 0.f;
+        for (int d = 0; d < hd; d += 8) {
+          const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
+          acc += bf16_lo(kv.x) * xq[d] + bf16_hi(kv.x) * xq[d + 1] + bf16_lo(kv.y) * xq[d + 2] +
+                 bf16_hi(kv.y) * xq[d + 3] + bf16_lo(kv.z) * xq[d + 4] + bf16_hi(kv.z) * xq[d + 5] +
+                 bf16_lo(kv.w) * xq[d + 6] + bf16_hi(kv.w) * xq[d + 7];
+        }
+        xs[j] = acc;
+        mx = fmaxf(mx, acc);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < p.Tk; j += 32) {
+        const float e = ua_exp2(xs[j] - mx);
+        xs[j] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      __syncwarp();
+      const float inv = 1.f / sum;
+      for (int d0 = 0; d0 < hd; d0 += 64) {
+        const int d = d0 + 2 * lane;   // each lane owns a bf16 pair
+        if (d < hd) {
+          float a0 = 0.f, a1 = 0.f;
+          for (int j = 0; j < p.Tk; ++j) {
+            const uint32_t vv = *reinterpret_cast<const uint32_t*>(vb + static_cast<long long>(j) * p.ldv + d);
+            a0 = fmaf(xs[j], bf16_lo(vv), a0);
+            a1 = fmaf(xs[j], bf16_hi(vv), a1);
+          }
+          *reinterpret_cast<uint32_t*>(p.o + qrow_base * p.ldo + hcol + d) = pack_bf16x2(a0 * inv, a1 * inv);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax + epilogue, thread = row
+    const int qt = (warp - 4) >> 2;
+    if (qt < p.n_qtiles) {
+      const int r = (warp & 3) * 32 + lane;
+      const int q_main = qt * 128 + r;                 // index among the main query rows
+      const bool row_ok = q_main < Tq_main;
+      const int q_abs = E + q_main;
+      const int offs = p.Tk - p.Tq;
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+      // score against the extra key on CUDA cores (overlaps the TMA + S MMAs)
+      float s_x = -INFINITY;
+      if (E && row_ok) {
+        const __nv_bfloat16* qr = p.q + (qrow_base + q_abs) * p.ldq + hcol;
+        float acc = 0.f;
+        for (int d = 0; d < hd; d += 8) {
+          const uint4 qv = *reinterpret_cast<const uint4*>(qr + d);
+          acc += bf16_lo(qv.x) * xk[d] + bf16_hi(qv.x) * xk[d + 1] + bf16_lo(qv.y) * xk[d + 2] +
+                 bf16_hi(qv.y) * xk[d + 3] + bf16_lo(qv.z) * xk[d + 4] + bf16_hi(qv.z) * xk[d + 5] +
+                 bf16_lo(qv.w) * xk[d + 6] + bf16_hi(qv.w) * xk[d + 7];
+        }
+        s_x = acc;
+      }
+      mbar_wait(&bar_s[qt], 0);
+      tcgen05_fence_after();
+      const uint32_t s_addr = t_lane + qt * 256;
+      // pass 1: row max of the raw scores (mask: padded keys, causal)
+      const int kmax = p.causal ? min(Tk_main, q_abs + offs + 1 - E) : Tk_main;   // main keys [0, kmax) visible
+      float mx = s_x;
+      for (int c = 0; c < p.nk_pad; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(s_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c + i < kmax) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      if (mx == -INFINITY) mx = 0.f;
+      const float neg_ms = -mx * p.scale_log2e;
+      // P may only overwrite K / Q once BOTH S products have been issued and retired
+      for (int t = 0; t < p.n_qtiles; ++t) mbar_wait(&bar_s[t], 0);
+      uint8_t* sP = qt == 0 ? sK : sQ;
+      float sum = 0.f;
+      for (int c = 0; c < p.nk_pad; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(s_addr + c, v);
+        tmem_ld_wait();
+        float e[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          e[i] = (c + i < kmax) ? ua_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2e, neg_ms)) : 0.f;
+          sum += e[i];
+        }
+        // two 16-byte chunks of the K-major, 128B-swizzled P tile
+        const int st = c >> 6, j0 = (c & 63) >> 3;
+        uint8_t* rowp = sP + st * SUB + r * 128;
+        *reinterpret_cast<uint4*>(rowp + (((j0) ^ (r & 7)) << 4)) =
+            make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+        *reinterpret_cast<uint4*>(rowp + (((j0 + 1) ^ (r & 7)) << 4)) =
+            make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
+      }
+      float p_x = 0.f;
+      if (E && row_ok) {
+        p_x = ua_exp2(fmaf(s_x, p.scale_log2e, neg_ms));
+        sum += p_x;
+      }
+      fence_proxy_async();        // P (generic-proxy stores) -> visible to the tensor core
+      tcgen05_fence_before();     // this thread's TMEM reads of S are done before O may overwrite them
+      mbar_arrive(&bar_p[qt]);
+      // ---- epilogue
+      mbar_wait(&bar_o[qt], 0);
+      tcgen05_fence_after();
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      const uint32_t o_addr = t_lane + (qt == 0 ? o_col0 : 256u);
+      __nv_bfloat16* orow = p.o + (qrow_base + q_abs) * p.ldo + hcol;
+      for (int c = 0; c < hd; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(o_addr + c, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = (__uint_as_float(v[i]) + p_x * xv[(c + i) & 127]) * inv;
+          *reinterpret_cast<uint4*>(orow + c) =
+              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          if (c + 8 < hd)
+            *reinterpret_cast<uint4*>(orow + c + 8) =
+                make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn2 encode_fn() {
+  static EncodeTiledFn2 fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn2>(ptr);
+  return fn;
+}
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
+                    int box_rows) {
+  EncodeTiledFn2 fn = encode_fn();
+  CGPT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CGPT_REQUIRE(r == CUDA_SUCCESS, "attention: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d",
+               (int)r, rows, cols, ld, box_cols, box_rows);
+  return 0;
+}
+
+// 1 = this shape is served by the tcgen05 kernel
+int attn_umma_supported(const cgpt_attn_args* a) {
+  if (a->decode_kernel != 0 || a->P != 0) return 0;
+  if (a->head_dim <= 64 || a->head_dim > 128 || (a->head_dim & 7)) return 0;
+  if (a->B * (long long)a->H > 0x7fffffffLL) return 0;
+  int E = 0;
+  if (a->Tk > 256) {
+    if (a->Tk - 1 > 256 || a->Tq != a->Tk || a->causal) return 0;
+    E = 1;
+  }
+  if (a->Tq - E > 256 || a->Tq - E < 1) return 0;
+  if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v)) & 15) return 0;
+  return 1;
+}
+
+int attention_umma(const cgpt_attn_args* a, cudaStream_t stream) {
+  UmmaAttnParams p;
+  p.q = (const __nv_bfloat16*)a->q; p.ldq = a->ldq; p.q_rows_per_batch = a->q_rows_per_batch;
+  p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v; p.ldk = a->ldk; p.ldv = a->ldv;
+  p.kv_rows_per_batch = a->kv_rows_per_batch;
+  p.o = (__nv_bfloat16*)a->o; p.ldo = a->ldo;
+  p.H = a->H; p.head_dim = a->head_dim; p.Tq = a->Tq; p.Tk = a->Tk; p.causal = a->causal;
+  p.E = a->Tk > 256 ? 1 : 0;
+  p.scale_log2e = a->scale * 1.4426950408889634f;
+  const int tq_main = a->Tq - p.E, tk_main = a->Tk - p.E;
+  p.n_qtiles = (tq_main + 127) / 128;
+  p.nk_pad = (tk_main + 15) / 16 * 16;
+  if (p.n_qtiles == 2) { p.tmem_cols = 512; p.o_col1 = 0; }
+  else if (p.nk_pad <= 128) { p.tmem_cols = 256; p.o_col1 = 128; }
+  else { p.tmem_cols = 512; p.o_col1 = 256; }
+  p.q_bytes = p.n_qtiles * 2 * SUB;
+  const int kv_sub = p.nk_pad * 128;
+  const int p_bytes = (p.nk_pad + 63) / 64 * SUB;
+  p.k_region = 2 * kv_sub > p_bytes ? 2 * kv_sub : p_bytes;
+  const int smem = p.q_bytes + p.k_region + 2 * kv_sub + 128 + 4 * 128 * 4 + 320 * 4 + 1024;
+  CGPT_REQUIRE(smem <= 227 * 1024, "attention_umma: shared memory %d too large", smem);
+
+  const long long q_rows = (long long)a->B * a->q_rows_per_batch, kv_rows = (long long)a->B * a->kv_rows_per_batch;
+  const long long cols = (long long)a->H * a->head_dim;
+  CUtensorMap mq0, mq1, mk, mv;
+  if (int rc = make_map(&mq0, a->q, q_rows, cols, a->ldq, 64, 128)) return rc;
+  if (int rc = make_map(&mq1, a->q, q_rows, cols, a->ldq, a->head_dim - 64, 128)) return rc;
+  if (int rc = make_map(&mk, a->k, kv_rows, cols, a->ldk, 64, p.nk_pad)) return rc;
+  if (int rc = make_map(&mv, a->v, kv_rows, cols, a->ldv, 64, p.nk_pad)) return rc;
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    CGPT_CHECK_CUDA(cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_smem = smem;
+  }
+  attn_umma_kernel<<<a->B * a->H, UA_THREADS, smem, stream>>>(mq0, mq1, mk, mv, p);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace cgpt

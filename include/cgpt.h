@@ -142,7 +142,8 @@ typedef struct cgpt_attn_args {
   int B, H, Tq, Tk, head_dim;
   float scale;
   int causal;
-  int decode_kernel; /* Tq == 1: use the single-token KV-cache kernel */
+  int decode_kernel; /* kernel selector: 0 = auto (tcgen05 one-shot kernel when the shape allows, else the
+                        mma.sync flash kernel), 1 = single-token KV-cache kernel (Tq == 1), 2 = force flash */
 } cgpt_attn_args;
 int cgpt_attention(const cgpt_attn_args* args, void* stream);
 
