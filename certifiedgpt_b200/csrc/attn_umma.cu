@@ -15,6 +15,7 @@
 // computed by a spare warp, so every tensor-core tile is exactly 128 x 256.
 // hd = 88 is not a multiple of the UMMA K (16): Q's columns 88..95 are zeroed in shared memory, so
 // whatever K holds there (the next head's finite values) contributes nothing.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ops.h"
 
@@ -29,6 +30,7 @@ struct UmmaAttnParams {
   int n_qtiles, nk_pad;                // 128-row query tiles; main keys padded to a multiple of 16
   int tmem_cols, o_col1;               // TMEM allocation; column of O for q-tile 0 when it does not alias S
   int q_bytes, k_region;               // smem carve-up
+  long long* dbg;                      // optional per-CTA phase timestamps [grid][16] (null in production)
 };
 
 constexpr int UA_THREADS = 384;
@@ -68,14 +70,18 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
   uint64_t* bar_s = bars + 2;    // [2] S_qt in TMEM
   uint64_t* bar_p = bars + 4;    // [2] P_qt in smem (128 arrivals)
   uint64_t* bar_o = bars + 6;    // [2] O_qt in TMEM
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_x = bars + 8;    // extra-query scores written (one arrival per softmax thread)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
   float* xk = reinterpret_cast<float*>(tail + 128);   // extra key   [128] fp32
   float* xv = xk + 128;                               // extra value [128]
   float* xq = xv + 128;                               // extra query [128], pre-scaled
-  float* xs = xq + 128;                               // extra-query scores [<= 288]
+  float* xs = xq + 128;                               // extra-query scores / probabilities [<= 320]
+  float* xo = xs + 320;                               // extra-query partial outputs [5][96]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
+#define UA_STAMP(slot) do { if (p.dbg) p.dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+  if (threadIdx.x == 0) UA_STAMP(0);
   const int hd = p.head_dim, E = p.E;
   const int Tk_main = p.Tk - E, Tq_main = p.Tq - E;
   const int hcol = h * hd;
@@ -89,6 +95,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
     mbar_init(bar_qk, 1);
     mbar_init(bar_v, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 128); mbar_init(&bar_o[i], 1); }
+    mbar_init(bar_x, 128 * p.n_qtiles);
     fence_barrier_init();
     fence_proxy_async();
     // ---- all loads of this (batch, head)
@@ -110,17 +117,30 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
   if (warp == 1) {
     tmem_alloc(tmem_ptr, p.tmem_cols);
     tmem_relinquish();
+    if (lane == 0) UA_STAMP(12);
   }
   if (warp == 3 && E) {
-    // extra (cls) key / value / query of this head as fp32 in shared memory
+    // extra (cls) key / value / query of this head as fp32 in shared memory (one 16-byte load per lane and row)
     const __nv_bfloat16* kx = p.k + krow_base * p.ldk + hcol;
     const __nv_bfloat16* vx = p.v + krow_base * p.ldv + hcol;
     const __nv_bfloat16* qx = p.q + qrow_base * p.ldq + hcol;
-    for (int d = lane; d < 128; d += 32) {
-      xk[d] = d < hd ? __bfloat162float(kx[d]) : 0.f;
-      xv[d] = d < hd ? __bfloat162float(vx[d]) : 0.f;
-      xq[d] = d < hd ? __bfloat162float(qx[d]) * p.scale_log2e : 0.f;
+    if (lane < 16) {
+      const bool ok = lane * 8 < hd;
+      uint4 a = make_uint4(0, 0, 0, 0), bq = a, c = a;
+      if (ok) {
+        a = *reinterpret_cast<const uint4*>(kx + lane * 8);
+        bq = *reinterpret_cast<const uint4*>(vx + lane * 8);
+        c = *reinterpret_cast<const uint4*>(qx + lane * 8);
+      }
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xk[lane * 8 + 2 * i] = bf16_lo(aw[i]); xk[lane * 8 + 2 * i + 1] = bf16_hi(aw[i]);
+        xv[lane * 8 + 2 * i] = bf16_lo(bw[i]); xv[lane * 8 + 2 * i + 1] = bf16_hi(bw[i]);
+        xq[lane * 8 + 2 * i] = bf16_lo(cw[i]) * p.scale_log2e; xq[lane * 8 + 2 * i + 1] = bf16_hi(cw[i]) * p.scale_log2e;
+      }
     }
+    if (lane == 0) UA_STAMP(15);
   }
   if (warp >= 4 && (hd & 15)) {
     // zero Q's pad columns [hd, roundup16(hd)) of the second sub-tile: one 16-byte chunk per row.
@@ -134,11 +154,28 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       fence_proxy_async();
     }
   }
+  // softmax threads prefetch their own Q row and K row (extra-key / extra-query dot products) so the
+  // global latency hides behind the setup barrier
+  uint4 pre_q[16], pre_k[16];
+  if (warp >= 4 && E) {
+    const int qtp = (warp - 4) >> 2;
+    const int rp = qtp * 128 + (warp & 3) * 32 + lane;
+    const bool okq = qtp < p.n_qtiles && rp < Tq_main, okk = qtp < p.n_qtiles && rp < Tk_main;
+    const __nv_bfloat16* qr = p.q + (qrow_base + E + rp) * p.ldq + hcol;
+    const __nv_bfloat16* kr = p.k + (krow_base + E + rp) * p.ldk + hcol;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      pre_q[c] = (okq && c * 8 < hd) ? *reinterpret_cast<const uint4*>(qr + c * 8) : make_uint4(0, 0, 0, 0);
+      pre_k[c] = (okk && c * 8 < hd) ? *reinterpret_cast<const uint4*>(kr + c * 8) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  if (warp == 0 && lane == 0) UA_STAMP(14);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t o_col0 = p.n_qtiles == 2 ? 0u : static_cast<uint32_t>(p.o_col1);
+  if (threadIdx.x == 0) UA_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -146,6 +183,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       const uint32_t idesc_s = make_idesc_bf16(128, p.nk_pad);
       const uint32_t idesc_o = make_idesc_bf16(128, 128) | (1u << 16);   // B (= V) is MN-major
       mbar_wait(bar_qk, 0);
+      UA_STAMP(2);
       tcgen05_fence_after();
       for (int qt = 0; qt < p.n_qtiles; ++qt) {
         const uint32_t d_tmem = tmem_base + qt * 256;
@@ -156,9 +194,11 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
         }
         umma_commit(&bar_s[qt]);
       }
+      UA_STAMP(3);
       mbar_wait(bar_v, 0);
       for (int qt = 0; qt < p.n_qtiles; ++qt) {
         mbar_wait(&bar_p[qt], 0);
+        UA_STAMP(4 + qt);
         tcgen05_fence_after();
         const uint8_t* sP = qt == 0 ? sK : sQ;
         const uint32_t d_tmem = tmem_base + (qt == 0 ? o_col0 : 256u);
@@ -170,45 +210,64 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
         umma_commit(&bar_o[qt]);
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == 2 || warp == 3) {
     // ---------------------------------------------------------------- extra (cls) query row, CUDA cores
+    // scores against the main keys come from the softmax threads (thread j <-> key j, xs[1 + j]);
+    // softmax over the Tk scores by warp 2, then P.V as a GEMV out of the V tile in shared memory
     if (E) {
-      const __nv_bfloat16* kb = p.k + krow_base * p.ldk + hcol;
-      const __nv_bfloat16* vb = p.v + krow_base * p.ldv + hcol;
-      float mx = -INFINITY;
-      for (int j = lane; j < p.Tk; j += 32) {
-        const __nv_bfloat16* kr = kb + static_cast<long long>(j) * p.ldk;
+      const int t64 = threadIdx.x - 64;   // 0..63
+      if (t64 == 0) {
         float acc = 0.f;
-        for (int d = 0; d < hd; d += 8) {
-          const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
-          acc += bf16_lo(kv.x) * xq[d] + bf16_hi(kv.x) * xq[d + 1] + bf16_lo(kv.y) * xq[d + 2] +
-                 bf16_hi(kv.y) * xq[d + 3] + bf16_lo(kv.z) * xq[d + 4] + bf16_hi(kv.z) * xq[d + 5] +
-                 bf16_lo(kv.w) * xq[d + 6] + bf16_hi(kv.w) * xq[d + 7];
-        }
-        xs[j] = acc;
-        mx = fmaxf(mx, acc);
+        for (int d = 0; d < hd; ++d) acc = fmaf(xq[d], xk[d], acc);
+        xs[0] = acc;                       // cls query . cls key
       }
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int j = lane; j < p.Tk; j += 32) {
-        const float e = ua_exp2(xs[j] - mx);
-        xs[j] = e;
-        sum += e;
-      }
-      sum = warp_sum(sum);
-      __syncwarp();
-      const float inv = 1.f / sum;
-      for (int d0 = 0; d0 < hd; d0 += 64) {
-        const int d = d0 + 2 * lane;   // each lane owns a bf16 pair
-        if (d < hd) {
-          float a0 = 0.f, a1 = 0.f;
-          for (int j = 0; j < p.Tk; ++j) {
-            const uint32_t vv = *reinterpret_cast<const uint32_t*>(vb + static_cast<long long>(j) * p.ldv + d);
-            a0 = fmaf(xs[j], bf16_lo(vv), a0);
-            a1 = fmaf(xs[j], bf16_hi(vv), a1);
-          }
-          *reinterpret_cast<uint32_t*>(p.o + qrow_base * p.ldo + hcol + d) = pack_bf16x2(a0 * inv, a1 * inv);
+      mbar_wait(bar_x, 0);
+      asm volatile("bar.sync 2, 64;" ::: "memory");
+      if (warp == 2) {
+        float mx = -INFINITY;
+        for (int j = lane; j < p.Tk; j += 32) mx = fmaxf(mx, xs[j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < p.Tk; j += 32) {
+          const float e = ua_exp2(xs[j] - mx);
+          xs[j] = e;
+          sum += e;
         }
+        sum = warp_sum(sum);
+        if (lane == 0) xs[p.Tk] = 1.f / sum;
+      }
+      mbar_wait(bar_v, 0);
+      asm volatile("bar.sync 2, 64;" ::: "memory");
+      // 11 (hd/8) column chunks x 5 key partitions = 55 threads
+      const int nch = hd >> 3;
+      const int c = t64 % nch, part = t64 / nch;
+      if (part < 5) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int per = (Tk_main + 4) / 5;
+        const int j0 = part * per, j1 = min(Tk_main, j0 + per);
+        const uint8_t* vsub = sV + (c >> 3) * kv_sub;
+        for (int j = j0; j < j1; ++j) {
+          const uint4 vv = *reinterpret_cast<const uint4*>(vsub + j * 128 + (((c & 7) ^ (j & 7)) << 4));
+          const float pj = xs[1 + j];
+          acc[0] = fmaf(pj, bf16_lo(vv.x), acc[0]); acc[1] = fmaf(pj, bf16_hi(vv.x), acc[1]);
+          acc[2] = fmaf(pj, bf16_lo(vv.y), acc[2]); acc[3] = fmaf(pj, bf16_hi(vv.y), acc[3]);
+          acc[4] = fmaf(pj, bf16_lo(vv.z), acc[4]); acc[5] = fmaf(pj, bf16_hi(vv.z), acc[5]);
+          acc[6] = fmaf(pj, bf16_lo(vv.w), acc[6]); acc[7] = fmaf(pj, bf16_hi(vv.w), acc[7]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xo[part * 96 + c * 8 + i] = acc[i];
+      }
+      asm volatile("bar.sync 2, 64;" ::: "memory");
+      if (t64 < nch) {
+        const float inv = xs[p.Tk];
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int d = t64 * 8 + i;
+          f[i] = (xo[d] + xo[96 + d] + xo[192 + d] + xo[288 + d] + xo[384 + d] + xs[0] * xv[d]) * inv;
+        }
+        *reinterpret_cast<uint4*>(p.o + qrow_base * p.ldo + hcol + t64 * 8) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
       }
     }
   } else if (warp >= 4) {
@@ -221,20 +280,28 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       const int q_abs = E + q_main;
       const int offs = p.Tk - p.Tq;
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-      // score against the extra key on CUDA cores (overlaps the TMA + S MMAs)
+      // scores against the extra key (this row) and of the extra query against main key q_main
+      // (thread <-> key), from the rows prefetched above; padded chunks are zero
       float s_x = -INFINITY;
-      if (E && row_ok) {
-        const __nv_bfloat16* qr = p.q + (qrow_base + q_abs) * p.ldq + hcol;
-        float acc = 0.f;
-        for (int d = 0; d < hd; d += 8) {
-          const uint4 qv = *reinterpret_cast<const uint4*>(qr + d);
-          acc += bf16_lo(qv.x) * xk[d] + bf16_hi(qv.x) * xk[d + 1] + bf16_lo(qv.y) * xk[d + 2] +
-                 bf16_hi(qv.y) * xk[d + 3] + bf16_lo(qv.z) * xk[d + 4] + bf16_hi(qv.z) * xk[d + 5] +
-                 bf16_lo(qv.w) * xk[d + 6] + bf16_hi(qv.w) * xk[d + 7];
+      if (E) {
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float* kk = xk + c * 8;
+          const float* qq = xq + c * 8;
+          const uint4 qv = pre_q[c], kv = pre_k[c];
+          a1 += bf16_lo(qv.x) * kk[0] + bf16_hi(qv.x) * kk[1] + bf16_lo(qv.y) * kk[2] + bf16_hi(qv.y) * kk[3] +
+                bf16_lo(qv.z) * kk[4] + bf16_hi(qv.z) * kk[5] + bf16_lo(qv.w) * kk[6] + bf16_hi(qv.w) * kk[7];
+          a2 += bf16_lo(kv.x) * qq[0] + bf16_hi(kv.x) * qq[1] + bf16_lo(kv.y) * qq[2] + bf16_hi(kv.y) * qq[3] +
+                bf16_lo(kv.z) * qq[4] + bf16_hi(kv.z) * qq[5] + bf16_lo(kv.w) * qq[6] + bf16_hi(kv.w) * qq[7];
         }
-        s_x = acc;
+        if (row_ok) s_x = a1;
+        if (q_main < Tk_main) xs[1 + q_main] = a2;
+        mbar_arrive(bar_x);
       }
+      if (threadIdx.x == 128) UA_STAMP(6);
       mbar_wait(&bar_s[qt], 0);
+      if (threadIdx.x == 128) UA_STAMP(7);
       tcgen05_fence_after();
       const uint32_t s_addr = t_lane + qt * 256;
       // pass 1: row max of the raw scores (mask: padded keys, causal)
@@ -249,6 +316,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
           if (c + i < kmax) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
       if (mx == -INFINITY) mx = 0.f;
+      if (threadIdx.x == 128) UA_STAMP(8);
       const float neg_ms = -mx * p.scale_log2e;
       // P may only overwrite K / Q once BOTH S products have been issued and retired
       for (int t = 0; t < p.n_qtiles; ++t) mbar_wait(&bar_s[t], 0);
@@ -280,8 +348,10 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       fence_proxy_async();        // P (generic-proxy stores) -> visible to the tensor core
       tcgen05_fence_before();     // this thread's TMEM reads of S are done before O may overwrite them
       mbar_arrive(&bar_p[qt]);
+      if (threadIdx.x == 128) UA_STAMP(9);
       // ---- epilogue
       mbar_wait(&bar_o[qt], 0);
+      if (threadIdx.x == 128) UA_STAMP(10);
       tcgen05_fence_after();
       const float inv = sum > 0.f ? 1.f / sum : 0.f;
       const uint32_t o_addr = t_lane + (qt == 0 ? o_col0 : 256u);
@@ -293,7 +363,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
         if (row_ok) {
           float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = (__uint_as_float(v[i]) + p_x * xv[(c + i) & 127]) * inv;
+          for (int i = 0; i < 16; ++i) f[i] = (__uint_as_float(v[i]) + (E ? p_x * xv[(c + i) & 127] : 0.f)) * inv;
           *reinterpret_cast<uint4*>(orow + c) =
               make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
           if (c + 8 < hd)
@@ -303,12 +373,15 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       }
     }
   }
+  if (threadIdx.x == 128) UA_STAMP(11);
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) UA_STAMP(13);
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+#undef UA_STAMP
 }
 
 // ------------------------------------------------------------------ host
@@ -366,6 +439,7 @@ int attention_umma(const cgpt_attn_args* a, cudaStream_t stream) {
   p.H = a->H; p.head_dim = a->head_dim; p.Tq = a->Tq; p.Tk = a->Tk; p.causal = a->causal;
   p.E = a->Tk > 256 ? 1 : 0;
   p.scale_log2e = a->scale * 1.4426950408889634f;
+  p.dbg = reinterpret_cast<long long*>(getenv("CGPT_ATTN_DBG") ? strtoull(getenv("CGPT_ATTN_DBG"), nullptr, 0) : 0ull);
   const int tq_main = a->Tq - p.E, tk_main = a->Tk - p.E;
   p.n_qtiles = (tq_main + 127) / 128;
   p.nk_pad = (tk_main + 15) / 16 * 16;
@@ -376,7 +450,7 @@ int attention_umma(const cgpt_attn_args* a, cudaStream_t stream) {
   const int kv_sub = p.nk_pad * 128;
   const int p_bytes = (p.nk_pad + 63) / 64 * SUB;
   p.k_region = 2 * kv_sub > p_bytes ? 2 * kv_sub : p_bytes;
-  const int smem = p.q_bytes + p.k_region + 2 * kv_sub + 128 + 4 * 128 * 4 + 320 * 4 + 1024;
+  const int smem = p.q_bytes + p.k_region + 2 * kv_sub + 128 + 3 * 128 * 4 + 320 * 4 + 5 * 96 * 4 + 1024;
   CGPT_REQUIRE(smem <= 227 * 1024, "attention_umma: shared memory %d too large", smem);
 
   const long long q_rows = (long long)a->B * a->q_rows_per_batch, kv_rows = (long long)a->B * a->kv_rows_per_batch;
