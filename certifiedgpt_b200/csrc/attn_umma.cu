@@ -30,6 +30,7 @@ struct UmmaAttnParams {
   int n_qtiles, nk_pad;                // 128-row query tiles; main keys padded to a multiple of 16
   int tmem_cols, o_col1;               // TMEM allocation; column of O for q-tile 0 when it does not alias S
   int q_bytes, k_region;               // smem carve-up
+  int prefetch_distance;               // CTAs per wave (L2 prefetch looks two waves ahead), 0 = off
   long long* dbg;                      // optional per-CTA phase timestamps [grid][16] (null in production)
 };
 
@@ -55,7 +56,8 @@ __device__ __forceinline__ float ua_exp2(float x) {
 
 __global__ void __launch_bounds__(UA_THREADS, 1)
 attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
-                 const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                 const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_k1,
+                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_v1,
                  UmmaAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -101,18 +103,37 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
     // ---- all loads of this (batch, head)
     const int q1_cols = hd - 64;
     const uint32_t q_tx = static_cast<uint32_t>(p.n_qtiles) * (64 * 128 * 2 + q1_cols * 128 * 2);
-    const uint32_t kv_tx = 2u * 64 * p.nk_pad * 2;
-    mbar_arrive_expect_tx(bar_qk, q_tx + kv_tx);
+    // second sub-tile boxes: K needs columns up to roundup16(hd) (Q is zero beyond hd), V only hd
+    const int k1_cols = ((hd + 15) & ~15) - 64, v1_cols = hd - 64;
+    const uint32_t k_tx = static_cast<uint32_t>(64 + k1_cols) * p.nk_pad * 2;
+    const uint32_t v_tx = static_cast<uint32_t>(64 + v1_cols) * p.nk_pad * 2;
+    mbar_arrive_expect_tx(bar_qk, q_tx + k_tx);
     for (int qt = 0; qt < p.n_qtiles; ++qt) {
       const int row = static_cast<int>(qrow_base) + E + qt * 128;
       tma_load_2d(sQ + qt * 2 * SUB, &map_q0, bar_qk, hcol, row);
       tma_load_2d(sQ + qt * 2 * SUB + SUB, &map_q1, bar_qk, hcol + 64, row);
     }
     tma_load_2d(sK, &map_k, bar_qk, hcol, static_cast<int>(krow_base) + E);
-    tma_load_2d(sK + kv_sub, &map_k, bar_qk, hcol + 64, static_cast<int>(krow_base) + E);
-    mbar_arrive_expect_tx(bar_v, kv_tx);
+    tma_load_2d(sK + kv_sub, &map_k1, bar_qk, hcol + 64, static_cast<int>(krow_base) + E);
+    mbar_arrive_expect_tx(bar_v, v_tx);
     tma_load_2d(sV, &map_v, bar_v, hcol, static_cast<int>(krow_base) + E);
-    tma_load_2d(sV + kv_sub, &map_v, bar_v, hcol + 64, static_cast<int>(krow_base) + E);
+    tma_load_2d(sV + kv_sub, &map_v1, bar_v, hcol + 64, static_cast<int>(krow_base) + E);
+    // L2 prefetch for the (batch, head) that runs ~2 waves from now: a CTA's loads are latency-bound
+    // (one CTA per SM, no second CTA to overlap with), so turn its DRAM misses into L2 hits
+    const int ahead = static_cast<int>(blockIdx.x) + 2 * static_cast<int>(p.prefetch_distance);
+    if (p.prefetch_distance > 0 && ahead < static_cast<int>(gridDim.x)) {
+      const int hb = ahead / p.H, hh = ahead % p.H;
+      const int pc = hh * hd;
+      const int pq = hb * p.q_rows_per_batch + E, pk = hb * p.kv_rows_per_batch + E;
+      for (int qt = 0; qt < p.n_qtiles; ++qt) {
+        tma_prefetch_l2_2d(&map_q0, pc, pq + qt * 128);
+        tma_prefetch_l2_2d(&map_q1, pc + 64, pq + qt * 128);
+      }
+      tma_prefetch_l2_2d(&map_k, pc, pk);
+      tma_prefetch_l2_2d(&map_k1, pc + 64, pk);
+      tma_prefetch_l2_2d(&map_v, pc, pk);
+      tma_prefetch_l2_2d(&map_v1, pc + 64, pk);
+    }
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr, p.tmem_cols);
@@ -152,21 +173,6 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       uint8_t* dst = sQ + qt * 2 * SUB + SUB + r * 128 + ((chunk ^ (r & 7)) << 4);
       *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
       fence_proxy_async();
-    }
-  }
-  // softmax threads prefetch their own Q row and K row (extra-key / extra-query dot products) so the
-  // global latency hides behind the setup barrier
-  uint4 pre_q[16], pre_k[16];
-  if (warp >= 4 && E) {
-    const int qtp = (warp - 4) >> 2;
-    const int rp = qtp * 128 + (warp & 3) * 32 + lane;
-    const bool okq = qtp < p.n_qtiles && rp < Tq_main, okk = qtp < p.n_qtiles && rp < Tk_main;
-    const __nv_bfloat16* qr = p.q + (qrow_base + E + rp) * p.ldq + hcol;
-    const __nv_bfloat16* kr = p.k + (krow_base + E + rp) * p.ldk + hcol;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      pre_q[c] = (okq && c * 8 < hd) ? *reinterpret_cast<const uint4*>(qr + c * 8) : make_uint4(0, 0, 0, 0);
-      pre_k[c] = (okk && c * 8 < hd) ? *reinterpret_cast<const uint4*>(kr + c * 8) : make_uint4(0, 0, 0, 0);
     }
   }
   if (warp == 0 && lane == 0) UA_STAMP(14);
@@ -281,22 +287,31 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       const int offs = p.Tk - p.Tq;
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
       // scores against the extra key (this row) and of the extra query against main key q_main
-      // (thread <-> key), from the rows prefetched above; padded chunks are zero
+      // (thread <-> key), read from the TMA-loaded, swizzled Q / K tiles in shared memory while the
+      // S products run; both tiles are still intact (P is written only after pass 1)
       float s_x = -INFINITY;
       if (E) {
+        mbar_wait(bar_qk, 0);
         float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float* kk = xk + c * 8;
-          const float* qq = xq + c * 8;
-          const uint4 qv = pre_q[c], kv = pre_k[c];
-          a1 += bf16_lo(qv.x) * kk[0] + bf16_hi(qv.x) * kk[1] + bf16_lo(qv.y) * kk[2] + bf16_hi(qv.y) * kk[3] +
-                bf16_lo(qv.z) * kk[4] + bf16_hi(qv.z) * kk[5] + bf16_lo(qv.w) * kk[6] + bf16_hi(qv.w) * kk[7];
-          a2 += bf16_lo(kv.x) * qq[0] + bf16_hi(kv.x) * qq[1] + bf16_lo(kv.y) * qq[2] + bf16_hi(kv.y) * qq[3] +
-                bf16_lo(kv.z) * qq[4] + bf16_hi(kv.z) * qq[5] + bf16_lo(kv.w) * qq[6] + bf16_hi(kv.w) * qq[7];
+        const int nch = hd >> 3;
+        const uint8_t* qrow = sQ + qt * 2 * SUB + r * 128;
+        const uint8_t* krow = sK + q_main * 128;        // key index == q_main (requires q_main < nk_pad)
+        const bool kok = q_main < Tk_main;
+        for (int c = 0; c < nch; ++c) {
+          const int sub = c >> 3, cc = c & 7;
+          const uint4 qv = *reinterpret_cast<const uint4*>(qrow + sub * SUB + ((cc ^ (r & 7)) << 4));
+          const float4 k0 = *reinterpret_cast<const float4*>(xk + c * 8), k1 = *reinterpret_cast<const float4*>(xk + c * 8 + 4);
+          a1 += bf16_lo(qv.x) * k0.x + bf16_hi(qv.x) * k0.y + bf16_lo(qv.y) * k0.z + bf16_hi(qv.y) * k0.w +
+                bf16_lo(qv.z) * k1.x + bf16_hi(qv.z) * k1.y + bf16_lo(qv.w) * k1.z + bf16_hi(qv.w) * k1.w;
+          if (kok) {
+            const uint4 kv = *reinterpret_cast<const uint4*>(krow + sub * kv_sub + ((cc ^ (q_main & 7)) << 4));
+            const float4 q0 = *reinterpret_cast<const float4*>(xq + c * 8), q1 = *reinterpret_cast<const float4*>(xq + c * 8 + 4);
+            a2 += bf16_lo(kv.x) * q0.x + bf16_hi(kv.x) * q0.y + bf16_lo(kv.y) * q0.z + bf16_hi(kv.y) * q0.w +
+                  bf16_lo(kv.z) * q1.x + bf16_hi(kv.z) * q1.y + bf16_lo(kv.w) * q1.z + bf16_hi(kv.w) * q1.w;
+          }
         }
         if (row_ok) s_x = a1;
-        if (q_main < Tk_main) xs[1 + q_main] = a2;
+        if (kok) xs[1 + q_main] = a2;
         mbar_arrive(bar_x);
       }
       if (threadIdx.x == 128) UA_STAMP(6);
@@ -304,16 +319,36 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       if (threadIdx.x == 128) UA_STAMP(7);
       tcgen05_fence_after();
       const uint32_t s_addr = t_lane + qt * 256;
-      // pass 1: row max of the raw scores (mask: padded keys, causal)
+      // pass 1: row max of the raw scores (mask: padded keys, causal).  16-column TMEM loads, the next one
+      // in flight while the current is reduced; full chunks skip the mask.
       const int kmax = p.causal ? min(Tk_main, q_abs + offs + 1 - E) : Tk_main;   // main keys [0, kmax) visible
       float mx = s_x;
-      for (int c = 0; c < p.nk_pad; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(s_addr + c, v);
-        tmem_ld_wait();
+      {
+        uint32_t va[16], vb[16];
+        tmem_ld_x16(s_addr, va);
+#pragma unroll 1
+        for (int c = 0; c < p.nk_pad; c += 32) {
+          tmem_ld_wait();
+          if (c + 16 < p.nk_pad) tmem_ld_x16(s_addr + c + 16, vb);
+          if (c + 16 <= kmax) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c + i < kmax) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c + i < kmax) mx = fmaxf(mx, __uint_as_float(va[i]));
+          }
+          if (c + 16 < p.nk_pad) {
+            tmem_ld_wait();
+            if (c + 32 < p.nk_pad) tmem_ld_x16(s_addr + c + 32, va);
+            if (c + 32 <= kmax) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) if (c + 16 + i < kmax) mx = fmaxf(mx, __uint_as_float(vb[i]));
+            }
+          }
+        }
       }
       if (mx == -INFINITY) mx = 0.f;
       if (threadIdx.x == 128) UA_STAMP(8);
@@ -322,16 +357,18 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       for (int t = 0; t < p.n_qtiles; ++t) mbar_wait(&bar_s[t], 0);
       uint8_t* sP = qt == 0 ? sK : sQ;
       float sum = 0.f;
-      for (int c = 0; c < p.nk_pad; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(s_addr + c, v);
-        tmem_ld_wait();
+      auto emit = [&](const uint32_t* v, int c) {
         float e[16];
+        if (c + 16 <= kmax) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          e[i] = (c + i < kmax) ? ua_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2e, neg_ms)) : 0.f;
-          sum += e[i];
+          for (int i = 0; i < 16; ++i) e[i] = ua_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2e, neg_ms));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            e[i] = (c + i < kmax) ? ua_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2e, neg_ms)) : 0.f;
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sum += e[i];
         // two 16-byte chunks of the K-major, 128B-swizzled P tile
         const int st = c >> 6, j0 = (c & 63) >> 3;
         uint8_t* rowp = sP + st * SUB + r * 128;
@@ -339,6 +376,21 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
             make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
         *reinterpret_cast<uint4*>(rowp + (((j0 + 1) ^ (r & 7)) << 4)) =
             make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
+      };
+      {
+        uint32_t va[16], vb[16];
+        tmem_ld_x16(s_addr, va);
+#pragma unroll 1
+        for (int c = 0; c < p.nk_pad; c += 32) {
+          tmem_ld_wait();
+          if (c + 16 < p.nk_pad) tmem_ld_x16(s_addr + c + 16, vb);
+          emit(va, c);
+          if (c + 16 < p.nk_pad) {
+            tmem_ld_wait();
+            if (c + 32 < p.nk_pad) tmem_ld_x16(s_addr + c + 32, va);
+            emit(vb, c + 16);
+          }
+        }
       }
       float p_x = 0.f;
       if (E && row_ok) {
@@ -356,19 +408,41 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       const float inv = sum > 0.f ? 1.f / sum : 0.f;
       const uint32_t o_addr = t_lane + (qt == 0 ? o_col0 : 256u);
       __nv_bfloat16* orow = p.o + (qrow_base + q_abs) * p.ldo + hcol;
-      for (int c = 0; c < hd; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(o_addr + c, v);
-        tmem_ld_wait();
-        if (row_ok) {
-          float f[16];
+      auto store16 = [&](const uint32_t* v, int c) {
+        if (!row_ok) return;
+        float f[16];
+        if (E) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = (__uint_as_float(v[i]) + (E ? p_x * xv[(c + i) & 127] : 0.f)) * inv;
-          *reinterpret_cast<uint4*>(orow + c) =
-              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-          if (c + 8 < hd)
-            *reinterpret_cast<uint4*>(orow + c + 8) =
-                make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+          for (int i = 0; i < 16; i += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xv + ((c + i) & 127));
+            f[i] = (__uint_as_float(v[i]) + p_x * x4.x) * inv;
+            f[i + 1] = (__uint_as_float(v[i + 1]) + p_x * x4.y) * inv;
+            f[i + 2] = (__uint_as_float(v[i + 2]) + p_x * x4.z) * inv;
+            f[i + 3] = (__uint_as_float(v[i + 3]) + p_x * x4.w) * inv;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv;
+        }
+        *reinterpret_cast<uint4*>(orow + c) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        if (c + 8 < hd)
+          *reinterpret_cast<uint4*>(orow + c + 8) =
+              make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+      };
+      {
+        uint32_t va[16], vb[16];
+        tmem_ld_x16(o_addr, va);
+#pragma unroll 1
+        for (int c = 0; c < hd; c += 32) {
+          tmem_ld_wait();
+          if (c + 16 < hd) tmem_ld_x16(o_addr + c + 16, vb);
+          store16(va, c);
+          if (c + 16 < hd) {
+            tmem_ld_wait();
+            if (c + 32 < hd) tmem_ld_x16(o_addr + c + 32, va);
+            store16(vb, c + 16);
+          }
         }
       }
     }
@@ -439,6 +513,12 @@ int attention_umma(const cgpt_attn_args* a, cudaStream_t stream) {
   p.H = a->H; p.head_dim = a->head_dim; p.Tq = a->Tq; p.Tk = a->Tk; p.causal = a->causal;
   p.E = a->Tk > 256 ? 1 : 0;
   p.scale_log2e = a->scale * 1.4426950408889634f;
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    p.prefetch_distance = getenv("CGPT_ATTN_NO_PREFETCH") ? 0 : sms;
+  }
   p.dbg = reinterpret_cast<long long*>(getenv("CGPT_ATTN_DBG") ? strtoull(getenv("CGPT_ATTN_DBG"), nullptr, 0) : 0ull);
   const int tq_main = a->Tq - p.E, tk_main = a->Tk - p.E;
   p.n_qtiles = (tq_main + 127) / 128;
@@ -455,17 +535,19 @@ int attention_umma(const cgpt_attn_args* a, cudaStream_t stream) {
 
   const long long q_rows = (long long)a->B * a->q_rows_per_batch, kv_rows = (long long)a->B * a->kv_rows_per_batch;
   const long long cols = (long long)a->H * a->head_dim;
-  CUtensorMap mq0, mq1, mk, mv;
+  CUtensorMap mq0, mq1, mk, mk1, mv, mv1;
   if (int rc = make_map(&mq0, a->q, q_rows, cols, a->ldq, 64, 128)) return rc;
   if (int rc = make_map(&mq1, a->q, q_rows, cols, a->ldq, a->head_dim - 64, 128)) return rc;
   if (int rc = make_map(&mk, a->k, kv_rows, cols, a->ldk, 64, p.nk_pad)) return rc;
   if (int rc = make_map(&mv, a->v, kv_rows, cols, a->ldv, 64, p.nk_pad)) return rc;
+  if (int rc = make_map(&mk1, a->k, kv_rows, cols, a->ldk, ((a->head_dim + 15) & ~15) - 64, p.nk_pad)) return rc;
+  if (int rc = make_map(&mv1, a->v, kv_rows, cols, a->ldv, a->head_dim - 64, p.nk_pad)) return rc;
   static int configured_smem = 0;
   if (smem > configured_smem) {
     CGPT_CHECK_CUDA(cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
   }
-  attn_umma_kernel<<<a->B * a->H, UA_THREADS, smem, stream>>>(mq0, mq1, mk, mv, p);
+  attn_umma_kernel<<<a->B * a->H, UA_THREADS, smem, stream>>>(mq0, mq1, mk, mk1, mv, mv1, p);
   CGPT_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -51,7 +51,7 @@ class MiniGPT4Engine:
         self.P = len(self.prefix_ids)
         self.Tp = cfg.qf.n_query + len(self.suffix_ids)      # per-sample prompt rows
         self.S = self.P + self.Tp                            # full prompt length
-        self.cache_rows = self.Tp + self.max_new_tokens
+        self.cache_rows = self.P + self.Tp + self.max_new_tokens   # [prefix | prompt rows | generated]
         self._pack(state_dict)
         self.table_keys, self.table_vals = L.build_answer_table(answer_table, cfg.llm.eos_id, self.dev)
         self._buf = {}
@@ -175,6 +175,13 @@ class MiniGPT4Engine:
             "margin": torch.zeros(B, self.max_new_tokens, dtype=f32, device=dev),
             "labels": torch.zeros(B, dtype=torch.int32, device=dev),
         }
+        # the batch-invariant prompt-prefix K/V (computed once, _build_prefix_cache) occupies rows [0, P) of
+        # every sample's cache: shared in compute, replicated in storage so attention reads one key range
+        if self.P > 0:
+            b["l.kc"][:, :, :self.P] = self.kp[:, None, :self.P]
+            b["l.vc"][:, :, :self.P] = self.vp[:, None, :self.P]
+        b["l.kc"][:, :, self.P:].zero_()
+        b["l.vc"][:, :, self.P:].zero_()
         self._buf, self._buf_B = b, B
         return b
 
@@ -246,7 +253,7 @@ class MiniGPT4Engine:
 
     # ------------------------------------------------------------------ Llama
     def _llm_layers(self, rows, T, B, res, xn, qkv, att, act, kc, vc, pos0, cache_row0, cache_rows,
-                    kp=None, vp=None, P=0, decode=False):
+                    decode=False):
         l, w = self.cfg.llm, self.w
         Hd = l.hidden
         scale = 1.0 / math.sqrt(l.head_dim)
@@ -256,10 +263,9 @@ class MiniGPT4Engine:
             L.gemm(xn, w[o + "qkv.w"], out=qkv)
             L.rope_split(qkv, T, l.heads, l.head_dim, pos0, w["rope.cos"], w["rope.sin"], kc[i], vc[i],
                          cache_rows, cache_row0)
-            Tk = P + cache_row0 + T
+            Tk = cache_row0 + T
             L.attention(qkv[:, :Hd], kc[i].view(-1, Hd), vc[i].view(-1, Hd), att, B=B, H=l.heads, Tq=T, Tk=Tk,
-                        head_dim=l.head_dim, scale=scale, kv_rows_per_batch=cache_rows, causal=True,
-                        kp=None if kp is None else kp[i], vp=None if vp is None else vp[i], P=P, decode=decode)
+                        head_dim=l.head_dim, scale=scale, kv_rows_per_batch=cache_rows, causal=True, decode=decode)
             L.gemm(att, w[o + "o.w"], resid=res, out=res)
             L.norm_rows(res, w[o + "n2"], None, l.rms_eps, xn, rms=True)
             L.gemm(xn, w[o + "gu.w"], act=L.ACT_SWIGLU, out=act)
@@ -300,8 +306,8 @@ class MiniGPT4Engine:
         if collect is not None:
             collect["llm_in"] = res.view(B, Tp, Hd).clone()
         # A12 prefill: per-sample rows attend to the shared prefix K/V + their own causal rows
-        self._llm_layers(M, Tp, B, res, xn, qkv, att, act, kc, vc, pos0=P, cache_row0=0,
-                         cache_rows=self.cache_rows, kp=self.kp, vp=self.vp, P=P)
+        self._llm_layers(M, Tp, B, res, xn, qkv, att, act, kc, vc, pos0=P, cache_row0=P,
+                         cache_rows=self.cache_rows)
         last, logits = buf["l.last"][:B], buf["l.logits"][:B]
         ids, fin, unf, nxt = buf["ids"][:B], buf["finished"][:B], buf["unfinished"], buf["next"][:B]
         margin = buf["margin"][:B]
@@ -326,7 +332,7 @@ class MiniGPT4Engine:
             # next token: embed, one-row-per-sample pass against the KV cache
             L.gather_rows(w["emb"], ids[:, t].contiguous(), B, dres, id_period=B)
             self._llm_layers(B, 1, B, dres, dxn, dqkv, datt, dact, kc, vc, pos0=P + Tp + t,
-                             cache_row0=Tp + t, cache_rows=self.cache_rows, kp=self.kp, vp=self.vp, P=P,
+                             cache_row0=P + Tp + t, cache_rows=self.cache_rows,
                              decode=l.head_dim in (32, 64, 128) and l.heads % 4 == 0)
             L.norm_rows(dres, w["llm.norm"], None, l.rms_eps, last, rms=True)
         self.last_steps = steps
