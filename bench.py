@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--max-new-tokens", type=int, default=4,
                     help="short-answer decode budget (BASELINE.md: ~3 decode steps per sample)")
-    ap.add_argument("--batch-size", type=int, default=1000)
+    ap.add_argument("--batch-size", type=int, default=1100)
     ap.add_argument("--img-size", type=int, default=224)
     ap.add_argument("--n0", type=int, default=N0)
     ap.add_argument("--n", type=int, default=N)

@@ -37,7 +37,7 @@ class Smooth(object):
 
     def __init__(self, base_classifier, num_classes: int, sigma: float, *, seed: int = 0,
                  noise_space: str = "normalized", noise_kind: str = "gaussian",
-                 mean=L.BLIP_MEAN, std=L.BLIP_STD, process_group=None):
+                 mean=L.BLIP_MEAN, std=L.BLIP_STD, process_group=None, fuse_selection: bool = True):
         """
         :param base_classifier: maps [batch x channel x height x width] to [batch x num_classes]
                (any torch.nn.Module), or a fused engine exposing `noisy_labels(...)`
@@ -52,6 +52,7 @@ class Smooth(object):
         self.noise_kind = _KIND[noise_kind]
         self.mean, self.std = tuple(mean), tuple(std)
         self.process_group = process_group
+        self.fuse_selection = fuse_selection
         self.image_id = 0          # Philox stream id; bumped per certify/predict call
         self._cursor = 0           # global sample index inside the current call
         self._injected = None
@@ -70,8 +71,14 @@ class Smooth(object):
         """Monte Carlo certification (smoothing.py:29-56).  Returns (class, radius) or (ABSTAIN, 0.0)."""
         self._eval()
         self._cursor = 0
-        counts_selection = self._sample_noise_device(x, n0, batch_size)
-        counts_estimation = self._sample_noise_device(x, n, batch_size)
+        if self.fuse_selection:
+            # The n0 selection draws and the n estimation draws are independent (fresh noise, smoothing.py:44,48)
+            # and keyed by global sample index, so both phases run as ONE sharded pass over [0, n0 + n) and are
+            # histogrammed into two count vectors: bit-identical counts, no small selection batch, one all-reduce.
+            counts_selection, counts_estimation = self._sample_noise_device(x, n0 + n, batch_size, split=n0)
+        else:
+            counts_selection = self._sample_noise_device(x, n0, batch_size)
+            counts_estimation = self._sample_noise_device(x, n, batch_size)
         lab, st = L.certify_tail(counts_selection, counts_estimation, n, alpha, self.sigma)
         label = int(lab[0].item())         # the one device->host read of the call
         radius = float(st[0].item())
@@ -130,22 +137,30 @@ class Smooth(object):
         assert e.shape[0] == count, "injected noise exhausted"
         return e.contiguous()
 
-    def _sample_noise_device(self, x, num: int, batch_size) -> torch.Tensor:
+    def _sample_noise_device(self, x, num: int, batch_size, split=None):
+        """Counts over the global sample range [cursor, cursor + num).  With `split`, samples
+        [cursor, cursor + split) are counted into a first vector and the rest into a second one."""
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
             raise L.CgptError("Smooth: x must be a CUDA tensor (no CPU path exists)")
         x = x.detach().to(torch.float32).contiguous()
         dev = x.device
         rank, world = rank_world(self.process_group)
         # this rank's contiguous slice of the global sample range [cursor, cursor + num)
-        lo, hi = shard_range(self._cursor, num, rank, world)
+        base = self._cursor
+        lo, hi = shard_range(base, num, rank, world)
         self._cursor += num
-        counts = torch.zeros(self.num_classes, dtype=torch.int64, device=dev)
+        nvec = 1 if split is None else 2
+        counts2 = torch.zeros(nvec, self.num_classes, dtype=torch.int64, device=dev)
+        counts = counts2[0]
+        boundary = base + split if split is not None else None
         invalid = torch.zeros(1, dtype=torch.int32, device=dev)
         fused = getattr(self.base_classifier, "noisy_labels", None)
         with torch.no_grad():
             first = lo
-            for _ in range(ceil((hi - lo) / batch_size)):
-                this_batch_size = min(batch_size, hi - first)
+            n_chunks = ceil((hi - lo) / batch_size) if hi > lo else 0
+            for ci in range(n_chunks):
+                # balanced chunks (each <= batch_size): no tiny tail batch
+                this_batch_size = (hi - first + (n_chunks - ci) - 1) // (n_chunks - ci)
                 eps = self._eps_for(first, this_batch_size)
                 kw = dict(eps=eps, seed=self.seed, stream_id=self.image_id, first_sample=first,
                           noise_space=self.noise_space, noise_kind=self.noise_kind)
@@ -157,10 +172,19 @@ class Smooth(object):
                     batch = L.noise_image(x, this_batch_size, self.sigma, mean=mean, std=std, **kw)
                     logits = self.base_classifier(batch)
                     labels = L.argmax_rows(logits.float().contiguous())
-                L.label_hist(labels, counts, invalid)
+                if boundary is None or first + this_batch_size <= boundary:
+                    L.label_hist(labels, counts2[0], invalid)
+                elif first >= boundary:
+                    L.label_hist(labels, counts2[1], invalid)
+                else:
+                    k = boundary - first
+                    L.label_hist(labels[:k], counts2[0], invalid)
+                    L.label_hist(labels[k:], counts2[1], invalid)
                 first += this_batch_size
         if world > 1:
-            allreduce_counts(counts, self.process_group)   # the only collective on the path
-        self.last_counts = counts
+            allreduce_counts(counts2, self.process_group)   # the only collective on the path
+        self.last_counts = counts2[0]
         self.last_invalid = invalid
-        return counts
+        if split is None:
+            return counts2[0]
+        return counts2[0], counts2[1]
