@@ -254,14 +254,20 @@ def run_ours(args, cfg):
 
     for _ in range(args.warmup):
         step_resident()
-    launches0 = L.launch_count()
-    L.gemm_profile_start()
+    launches0 = L.launch_count() + eng.replayed_launches
     with ClockSampler(local) as clocks:
         ms = timed(step_resident, args.steps)
-    prof = L.gemm_profile_stop()
-    launches = L.launch_count() - launches0
+    launches = L.launch_count() + eng.replayed_launches - launches0
     ms_e2e = timed(step_e2e, args.steps)
     result = step_resident()
+    # roofline pass: the same steps launched eagerly (not as graph replays) so that every GEMM launch can be
+    # bracketed by a CUDA-event pair on its stream; same kernels, same shapes, same data
+    eng.use_graphs = False
+    step_resident()
+    L.gemm_profile_start()
+    ms_prof = timed(step_resident, args.steps)
+    prof = L.gemm_profile_stop()
+    eng.use_graphs = True
 
     value = per_step * args.steps / (ms / 1e3)
     e2e = per_step * args.steps / (ms_e2e / 1e3)
@@ -309,7 +315,8 @@ def run_ours(args, cfg):
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the timed steps)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
-                         "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
+                         "gemm_share_of_step": gemm_ms / ms_prof if ms_prof > 0 else None,
+                         "measured_in": "eager replay of the timed steps (graph replays cannot be event-bracketed per kernel)",
                          "gemm_launches": len(prof),
                          "top_shapes": {k: {"ms": round(v[0], 3), "tflops": round(v[1] / (v[0] / 1e3) / 1e12, 1), "launches": v[2]}
                                         for k, v in top}},

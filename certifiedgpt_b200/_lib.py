@@ -89,6 +89,7 @@ def _EXTRA_SIGS(vp, i64, i32, f32, f64, u64):
     u32 = C.c_uint32
     return {
         "cgpt_noise_patchify": [vp, vp, u64, u32, u64, i32, f32, vp, vp, i32, i32, i32, vp, i64, vp],
+        "cgpt_noise_patchify_dyn": [vp, vp, i32, vp, vp, i32, i32, i32, vp, i64, vp],
         "cgpt_noise_image": [vp, vp, u64, u32, u64, i32, f32, vp, vp, i32, i32, i32, i32, i32, vp, vp],
         "cgpt_answer_labels": [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp],
         "cgpt_argmax_rows": [vp, i32, i32, i64, i32, vp, vp, vp],
@@ -209,6 +210,23 @@ def noise_patchify(x, B, sigma, *, eps=None, seed=0, stream_id=0, first_sample=0
                                   _f3(mean), _f3(std), noise_space, noise_kind, S, ptr(out),
                                   out.stride(0), stream_ptr()))
     return out
+
+
+def noise_patchify_dyn(x, dyn_params, B, *, noise_space=SPACE_NORMALIZED, noise_kind=NOISE_GAUSSIAN,
+                       mean=BLIP_MEAN, std=BLIP_STD, out=None):
+    """K1 with (seed, first_sample, stream_id, sigma) read from a 24-byte device struct (graph replay)."""
+    lib = load()
+    S = x.shape[-1]
+    check(lib.cgpt_noise_patchify_dyn(ptr(x), ptr(dyn_params), B, _f3(mean), _f3(std), noise_space,
+                                      noise_kind, S, ptr(out), out.stride(0), stream_ptr()))
+    return out
+
+
+def pack_noise_dyn(seed, first_sample, stream_id, sigma):
+    """Host bytes of the NoiseDyn struct (little endian: u64 seed, u64 first_sample, u32 stream_id, f32 sigma)."""
+    import struct
+    return struct.pack("<QQIf", int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_sample), int(stream_id) & 0xFFFFFFFF,
+                       float(sigma))
 
 
 def noise_image(x, B, sigma, *, eps=None, seed=0, stream_id=0, first_sample=0,

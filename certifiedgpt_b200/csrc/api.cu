@@ -34,7 +34,14 @@ int cgpt_noise_patchify(const float* x, const float* eps, uint64_t seed, uint32_
                         const float* std3, int noise_space, int noise_kind, int img_size,
                         void* out_patches, int64_t ld_out, void* stream) {
   return noise_patchify(x, eps, seed, stream_id, first_sample, B, sigma, mean3, std3, noise_space,
-                        noise_kind, img_size, out_patches, ld_out, (cudaStream_t)stream);
+                        noise_kind, img_size, out_patches, ld_out, nullptr, (cudaStream_t)stream);
+}
+int cgpt_noise_patchify_dyn(const float* x, const void* dyn_params, int B, const float* mean3,
+                            const float* std3, int noise_space, int noise_kind, int img_size,
+                            void* out_patches, int64_t ld_out, void* stream) {
+  CGPT_REQUIRE(dyn_params != nullptr, "noise_patchify_dyn: dyn_params is null");
+  return noise_patchify(x, nullptr, 0, 0, 0, B, 0.f, mean3, std3, noise_space, noise_kind, img_size,
+                        out_patches, ld_out, dyn_params, (cudaStream_t)stream);
 }
 int cgpt_noise_image(const float* x, const float* eps, uint64_t seed, uint32_t stream_id,
                      uint64_t first_sample, int B, float sigma, const float* mean3,

@@ -514,9 +514,12 @@ int attention_umma(const cgpt_attn_args* a, cudaStream_t stream) {
   p.E = a->Tk > 256 ? 1 : 0;
   p.scale_log2e = a->scale * 1.4426950408889634f;
   {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
     p.prefetch_distance = getenv("CGPT_ATTN_NO_PREFETCH") ? 0 : sms;
   }
   p.dbg = reinterpret_cast<long long*>(getenv("CGPT_ATTN_DBG") ? strtoull(getenv("CGPT_ATTN_DBG"), nullptr, 0) : 0ull);

@@ -63,6 +63,15 @@ __device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float& z0, 
   z1 = rad * s;
 }
 
+// per-batch parameters read from device memory (CUDA-graph replay: the kernel node is captured once,
+// the host rewrites this struct before every replay)
+struct NoiseDyn {
+  unsigned long long seed;
+  unsigned long long first_sample;
+  unsigned int stream_id;
+  float sigma;
+};
+
 struct NoiseParams {
   const float* x;      // [3,S,S]
   const float* eps;    // [B,3,S,S] injected standard draws, or null -> Philox
@@ -73,6 +82,7 @@ struct NoiseParams {
   float mean[4], stdv[4];
   int noise_space, noise_kind, S;
   long long per_img;   // elements per image (C*H*W)
+  const NoiseDyn* dyn; // optional override of (seed, first_sample, stream_id, sigma)
 };
 
 // noisy, normalised values of 4 consecutive pixels (c, y, x0..x0+3) of sample b (local index)
@@ -115,6 +125,9 @@ __device__ __forceinline__ float4 noisy4(const NoiseParams& p, int b, int c, lon
 
 __global__ void __launch_bounds__(256) noise_patchify_kernel(NoiseParams p, __nv_bfloat16* __restrict__ out,
                                                              long long ld_out) {
+  if (p.dyn != nullptr) {
+    p.seed = p.dyn->seed; p.first_sample = p.dyn->first_sample; p.stream_id = p.dyn->stream_id; p.sigma = p.dyn->sigma;
+  }
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [G][592]
   const int S = p.S;
@@ -191,6 +204,7 @@ static int fill_params(NoiseParams& p, const float* x, const float* eps, uint64_
                "noise: bad noise_kind %d", noise_kind);
   CGPT_REQUIRE(noise_space == CGPT_SPACE_NORMALIZED || (mean3 && std3),
                "noise: PIXEL space needs mean/std");
+  p.dyn = nullptr;
   p.x = x; p.eps = eps; p.seed = seed; p.stream_id = stream_id; p.first_sample = first_sample;
   p.sigma = sigma; p.noise_space = noise_space; p.noise_kind = noise_kind; p.S = img_size;
   for (int i = 0; i < 4; ++i) {
@@ -203,11 +217,12 @@ static int fill_params(NoiseParams& p, const float* x, const float* eps, uint64_
 int noise_patchify(const float* x, const float* eps, uint64_t seed, uint32_t stream_id,
                    uint64_t first_sample, int B, float sigma, const float* mean3,
                    const float* std3, int noise_space, int noise_kind, int img_size, void* out,
-                   long long ld_out, cudaStream_t stream) {
+                   long long ld_out, const void* dyn, cudaStream_t stream) {
   NoiseParams p;
   if (int rc = fill_params(p, x, eps, seed, stream_id, first_sample, B, sigma, mean3, std3,
                            noise_space, noise_kind, img_size, 3))
     return rc;
+  p.dyn = reinterpret_cast<const NoiseDyn*>(dyn);
   CGPT_REQUIRE(img_size > 0 && img_size % PATCH == 0 && img_size % 4 == 0,
                "noise_patchify: image size %d must be a multiple of 14 and of 4", img_size);
   p.per_img = 3LL * img_size * img_size;

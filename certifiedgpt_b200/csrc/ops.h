@@ -14,7 +14,7 @@ int gemm_launch_count();
 int noise_patchify(const float* x, const float* eps, uint64_t seed, uint32_t stream_id,
                    uint64_t first_sample, int B, float sigma, const float* mean3,
                    const float* std3, int noise_space, int noise_kind, int img_size, void* out,
-                   long long ld_out, cudaStream_t stream);
+                   long long ld_out, const void* dyn, cudaStream_t stream);
 int noise_image(const float* x, const float* eps, uint64_t seed, uint32_t stream_id,
                 uint64_t first_sample, int B, float sigma, const float* mean3, const float* std3,
                 int noise_space, int noise_kind, int channels, int height, int width, float* out,

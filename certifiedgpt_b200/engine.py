@@ -37,7 +37,8 @@ class MiniGPT4Engine:
     cgpt_fused = True
 
     def __init__(self, cfg: ModelConfig, state_dict, prefix_ids, suffix_ids, answer_table,
-                 num_classes, *, max_new_tokens=20, min_length=1, device="cuda", early_exit=True):
+                 num_classes, *, max_new_tokens=20, min_length=1, device="cuda", early_exit=True,
+                 use_graphs=True):
         L.load()
         self.cfg = cfg
         self.dev = torch.device(device)
@@ -56,6 +57,14 @@ class MiniGPT4Engine:
         self.table_keys, self.table_vals = L.build_answer_table(answer_table, cfg.llm.eos_id, self.dev)
         self._buf = {}
         self._buf_B = 0
+        # CUDA graphs: one graph for [noise .. first token] and one per decode step, per batch size; replayed
+        # with the per-batch noise parameters rewritten in device memory (no host launch cost, no gaps)
+        self.use_graphs = use_graphs
+        self._graphs = {}
+        self._graph_nodes = {}
+        self.replayed_launches = 0
+        self._x_static = None
+        self._dyn = torch.zeros(24, dtype=torch.uint8, device=self.dev)
         self._build_prefix_cache()
         self.last = {}
 
@@ -154,6 +163,7 @@ class MiniGPT4Engine:
             return torch.empty(*shape, dtype=dtype, device=dev)
 
         self._buf = None
+        self._graphs = {}          # captured graphs hold the old buffer addresses
         torch.cuda.empty_cache()
         b = {
             "patches": e(B * v.grid * v.grid, 592),
@@ -172,6 +182,8 @@ class MiniGPT4Engine:
             "finished": torch.zeros(B, dtype=torch.int32, device=dev),
             "unfinished": torch.zeros(1, dtype=torch.int32, device=dev),
             "next": torch.zeros(B, dtype=torch.int32, device=dev),
+            "cur": torch.zeros(B, dtype=torch.int32, device=dev),
+            "mcol": torch.zeros(B, dtype=f32, device=dev),
             "margin": torch.zeros(B, self.max_new_tokens, dtype=f32, device=dev),
             "labels": torch.zeros(B, dtype=torch.int32, device=dev),
         }
@@ -290,8 +302,8 @@ class MiniGPT4Engine:
                          pos0=0, cache_row0=0, cache_rows=P)
         torch.cuda.synchronize()
 
-    def llm_generate(self, B, buf, qf_out, collect=None):
-        """qf_out [B*n_query, qf.hidden] bf16 -> generated ids buf['ids'] [B, max_new] int32."""
+    def _llm_prefill_first(self, B, buf, qf_out, collect=None):
+        """llama_proj + prompt assembly + prefill + first greedy token (t = 0)."""
         cfg, w = self.cfg, self.w
         q, l = cfg.qf, cfg.llm
         nq, Tp, P, Hd = q.n_query, self.Tp, self.P, l.hidden
@@ -308,40 +320,59 @@ class MiniGPT4Engine:
         # A12 prefill: per-sample rows attend to the shared prefix K/V + their own causal rows
         self._llm_layers(M, Tp, B, res, xn, qkv, att, act, kc, vc, pos0=P, cache_row0=P,
                          cache_rows=self.cache_rows)
-        last, logits = buf["l.last"][:B], buf["l.logits"][:B]
-        ids, fin, unf, nxt = buf["ids"][:B], buf["finished"][:B], buf["unfinished"], buf["next"][:B]
-        margin = buf["margin"][:B]
+        last = buf["l.last"][:B]
+        ids, fin, margin = buf["ids"][:B], buf["finished"][:B], buf["margin"][:B]
         ids.fill_(l.pad_id)
         fin.zero_()
         margin.fill_(float("inf"))
         L.norm_rows(res, w["llm.norm"], None, l.rms_eps, last, rms=True, gather=(1, Tp, Tp - 1))
-        dres, dxn, dqkv, datt, dact = (buf[k][:B] for k in ("d.res", "d.xn", "d.qkv", "d.att", "d.act"))
-        steps = 0
-        for t in range(self.max_new_tokens):
-            L.gemm(last, w["llm.head"], out=logits)
-            if collect is not None and t == 0:
-                collect["first_logits"] = logits.clone()
-            self._argmax(logits, l.eos_id if t < self.min_length else -1, nxt, margin, t)
-            unf.zero_()
-            L.greedy_step(nxt, fin, ids, t, l.eos_id, l.pad_id, unf)
-            steps = t + 1
-            if t == self.max_new_tokens - 1:
-                break
-            if self.early_exit and int(unf.item()) == 0:
-                break
-            # next token: embed, one-row-per-sample pass against the KV cache
-            L.gather_rows(w["emb"], ids[:, t].contiguous(), B, dres, id_period=B)
-            self._llm_layers(B, 1, B, dres, dxn, dqkv, datt, dact, kc, vc, pos0=P + Tp + t,
-                             cache_row0=P + Tp + t, cache_rows=self.cache_rows,
-                             decode=l.head_dim in (32, 64, 128) and l.heads % 4 == 0)
-            L.norm_rows(dres, w["llm.norm"], None, l.rms_eps, last, rms=True)
-        self.last_steps = steps
-        return ids
+        self._head_and_pick(B, buf, 0, collect)
 
-    def _argmax(self, logits, suppress, nxt, margin, t):
+    def _head_and_pick(self, B, buf, t, collect=None):
+        """lm_head on the last hidden state, greedy pick with HF min_length / EOS / pad bookkeeping."""
+        l, w = self.cfg.llm, self.w
+        last, logits = buf["l.last"][:B], buf["l.logits"][:B]
+        ids, fin, unf, nxt = buf["ids"][:B], buf["finished"][:B], buf["unfinished"], buf["next"][:B]
+        L.gemm(last, w["llm.head"], out=logits)
+        if collect is not None and t == 0:
+            collect["first_logits"] = logits.clone()
+        self._argmax(logits, l.eos_id if t < self.min_length else -1, nxt, buf["margin"][:B], t, buf["mcol"][:B])
+        unf.zero_()
+        L.greedy_step(nxt, fin, ids, t, l.eos_id, l.pad_id, unf)
+
+    def _llm_decode_step(self, B, buf, t):
+        """Decode step t >= 1: embed token t-1, one row per sample against the KV cache, pick token t."""
+        l, w = self.cfg.llm, self.w
+        P, Tp = self.P, self.Tp
+        kc, vc = buf["l.kc"][:, :B], buf["l.vc"][:, :B]
+        dres, dxn, dqkv, datt, dact = (buf[k][:B] for k in ("d.res", "d.xn", "d.qkv", "d.att", "d.act"))
+        cur = buf["cur"][:B]
+        cur.copy_(buf["ids"][:B, t - 1])
+        L.gather_rows(w["emb"], cur, B, dres, id_period=B)
+        self._llm_layers(B, 1, B, dres, dxn, dqkv, datt, dact, kc, vc, pos0=P + Tp + t - 1,
+                         cache_row0=P + Tp + t - 1, cache_rows=self.cache_rows,
+                         decode=l.head_dim in (32, 64, 128) and l.heads % 4 == 0)
+        L.norm_rows(dres, w["llm.norm"], None, l.rms_eps, buf["l.last"][:B], rms=True)
+        self._head_and_pick(B, buf, t)
+
+    def _all_finished(self, buf):
+        return self.early_exit and int(buf["unfinished"].item()) == 0
+
+    def llm_generate(self, B, buf, qf_out, collect=None):
+        """qf_out [B*n_query, qf.hidden] bf16 -> generated ids buf['ids'] [B, max_new] int32 (eager path)."""
+        self._llm_prefill_first(B, buf, qf_out, collect)
+        steps = 1
+        for t in range(1, self.max_new_tokens):
+            if self._all_finished(buf):
+                break
+            self._llm_decode_step(B, buf, t)
+            steps = t + 1
+        self.last_steps = steps
+        return buf["ids"][:B]
+
+    def _argmax(self, logits, suppress, nxt, margin, t, mcol):
         lib = L.load()
         rows, cols = logits.shape
-        mcol = torch.empty(rows, dtype=torch.float32, device=logits.device)
         L.check(lib.cgpt_argmax_rows(L.ptr(logits), rows, cols, logits.stride(0), suppress, L.ptr(nxt),
                                      L.ptr(mcol), L.stream_ptr()))
         margin[:, t] = mcol
@@ -366,12 +397,83 @@ class MiniGPT4Engine:
                      noise_space=L.SPACE_NORMALIZED, noise_kind=L.NOISE_GAUSSIAN,
                      mean=L.BLIP_MEAN, std=L.BLIP_STD, collect=None):
         """One batch of the hot loop: labels[b] = f(x + sigma*eps_b), b = first_sample .. +B."""
+        if self.use_graphs and eps is None and collect is None:
+            return self._noisy_labels_graphed(x, B, sigma, seed, stream_id, first_sample, noise_space, noise_kind,
+                                              tuple(mean), tuple(std))
         buf = self._buffers(B)
         G2 = self.cfg.vit.grid ** 2
         L.noise_patchify(x, B, sigma, eps=eps, seed=seed, stream_id=stream_id, first_sample=first_sample,
                          noise_space=noise_space, noise_kind=noise_kind, mean=mean, std=std,
                          out=buf["patches"][:B * G2])
         return self.labels_from_patches(B, buf, collect)
+
+    # ------------------------------------------------------------------ CUDA-graph replay path
+    def _capture(self, B, key):
+        noise_space, noise_kind, mean, std = key[1:]
+        buf = self._buffers(B)
+        G2 = self.cfg.vit.grid ** 2
+
+        def stage0():
+            L.noise_patchify_dyn(self._x_static, self._dyn, B, noise_space=noise_space, noise_kind=noise_kind,
+                                 mean=mean, std=std, out=buf["patches"][:B * G2])
+            img = self.vit_from_patches(B, buf)
+            qo = self.qformer(B, buf, img)
+            self._llm_prefill_first(B, buf, qo)
+
+        # warm-up outside capture: first-use cudaFuncSetAttribute calls, allocator state
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            stage0()
+            for t in range(1, self.max_new_tokens):
+                self._llm_decode_step(B, buf, t)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        nodes = []
+        c0 = L.launch_count()
+        g0 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g0):
+            stage0()
+        nodes.append(L.launch_count() - c0)
+        steps = []
+        for t in range(1, self.max_new_tokens):
+            c0 = L.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=g0.pool()):
+                self._llm_decode_step(B, buf, t)
+            nodes.append(L.launch_count() - c0)
+            steps.append(g)
+        self._graph_nodes[key] = nodes     # libcgpt kernel nodes per graph (bench.py gpu_launches)
+        return g0, steps
+
+    def _noisy_labels_graphed(self, x, B, sigma, seed, stream_id, first_sample, noise_space, noise_kind, mean, std):
+        if self._x_static is None or self._x_static.shape != x.shape:
+            self._x_static = torch.empty_like(x)
+            self._graphs = {}
+        buf = self._buffers(B)
+        key = (B, noise_space, noise_kind, mean, std)
+        if key not in self._graphs:
+            self._graphs[key] = self._capture(B, key)
+            buf = self._buffers(B)
+        g0, steps = self._graphs[key]
+        if x.data_ptr() != self._x_static.data_ptr():
+            self._x_static.copy_(x, non_blocking=True)
+        # pageable source: the copy is staged before the call returns, so the host bytes can be reused at once
+        self._dyn.copy_(torch.frombuffer(bytearray(L.pack_noise_dyn(seed, first_sample, stream_id, sigma)),
+                                         dtype=torch.uint8))
+        g0.replay()
+        self.replayed_launches += self._graph_nodes[key][0]
+        n = 1
+        for t in range(1, self.max_new_tokens):
+            if self._all_finished(buf):
+                break
+            steps[t - 1].replay()
+            self.replayed_launches += self._graph_nodes[key][t]
+            n = t + 1
+        self.last_steps = n
+        ids, labels = buf["ids"][:B], buf["labels"][:B]
+        L.answer_labels(ids, self.table_keys, self.table_vals, self.other_label, self.cfg.llm.eos_id, out=labels)
+        return labels
 
     @torch.no_grad()
     def forward_images(self, images, collect=None):

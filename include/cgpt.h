@@ -79,6 +79,12 @@ int cgpt_noise_patchify(const float* x, const float* eps, uint64_t seed, uint32_
                         uint64_t first_sample, int B, float sigma, const float* mean3,
                         const float* std3, int noise_space, int noise_kind, int img_size,
                         void* out_patches, int64_t ld_out, void* stream);
+/* CUDA-graph friendly variant: (seed, first_sample, stream_id, sigma) are read from the device struct
+ * { uint64 seed; uint64 first_sample; uint32 stream_id; float sigma; } at dyn_params, so one captured
+ * kernel node serves every batch (the host rewrites the 24-byte struct before each replay) */
+int cgpt_noise_patchify_dyn(const float* x, const void* dyn_params, int B, const float* mean3,
+                            const float* std3, int noise_space, int noise_kind, int img_size,
+                            void* out_patches, int64_t ld_out, void* stream);
 /* same draw, NCHW fp32 output for an arbitrary torch base_classifier (smoothing.py:95-97) */
 int cgpt_noise_image(const float* x, const float* eps, uint64_t seed, uint32_t stream_id,
                      uint64_t first_sample, int B, float sigma, const float* mean3,

@@ -128,3 +128,20 @@ def test_full_width_llm_matches_oracle():
     safe = (orc.last["margins"] > 1e-2).all(dim=1)
     assert torch.equal(got["ids"].cpu().long()[safe], orc.last["ids"][safe])
     assert torch.equal(labels.cpu().long()[safe], orc.last["labels"][safe])
+
+
+def test_graph_replay_matches_eager(full_engine):
+    """CUDA-graph replay (per-batch noise parameters rewritten in device memory) produces the same labels
+    as the eager launch sequence, batch after batch."""
+    eng = full_engine
+    x = torch.rand(3, 224, 224, generator=torch.Generator().manual_seed(1002)).cuda()
+    outs = {}
+    for mode in (False, True, True):
+        eng.use_graphs = mode
+        res = []
+        for first in (0, 24, 48):
+            res.append(eng.noisy_labels(x, 24, 0.25, seed=9, stream_id=3, first_sample=first).clone())
+        outs.setdefault(mode, []).append(torch.cat(res))
+    eng.use_graphs = True
+    assert torch.equal(outs[False][0], outs[True][0]) and torch.equal(outs[True][0], outs[True][1])
+    assert eng.replayed_launches > 0
