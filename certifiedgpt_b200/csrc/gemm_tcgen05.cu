@@ -7,21 +7,28 @@
 // nn.Linear weight layout ([out,in]), so no transposes exist anywhere.
 //
 // Structure (one persistent CTA per SM, 256 threads):
-//   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled A/B k-blocks -> smem ring
-//   warp 1      MMA issuer     : one thread issues tcgen05.mma (UMMA 128 x BN x 16), fp32
+//   warp 8      TMA producer   : cp.async.bulk.tensor 128B-swizzled A/B k-blocks -> smem ring
+//   warp 9      MMA issuer     : one thread issues tcgen05.mma (UMMA 128 x BN x 16), fp32
 //                                accumulators in TMEM, two accumulator stages
-//   warp 2      TMEM allocator
-//   warps 4..11 epilogue       : 2 warps per TMEM lane quarter (column halves); software-pipelined
+//   warp 10     TMEM allocator
+//   (k-blocks are 128 wide = two swizzle atoms, 8 MMAs per barrier round trip: with 64-wide blocks the
+//    single issuing thread's wait/fence/commit chain left only ~13 % slack against the 512-cycle MMA
+//    time of a block, and an ALU-heavy epilogue (GELU) sharing its scheduler pushed it past that:
+//    14.0k instead of 11.3k cycles per 256x256x1408 tile, measured with CGPT_GEMM_DBG)
+//   warps 0..7  epilogue       : 2 warps per TMEM lane quarter (column halves); software-pipelined
 //                                tcgen05.ld -> bias (staged in smem) / GELU / SwiGLU / residual
 //                                (prefetched) / pos-embed -> bf16 or fp32 global stores, overlapped
 //                                with the next tile's MMAs through the second TMEM stage
+#include <stdlib.h>
 #include "common.cuh"
 #include "ops.h"
 
 namespace cgpt {
 
 constexpr int BM = 128;
-constexpr int BK = 64;
+constexpr int BK = 128;     // k-block per pipeline stage = KSUB swizzle atoms of 64 bf16
+constexpr int BKA = 64;     // one 128-byte swizzle atom along K (TMA box width)
+constexpr int KSUB = BK / BKA;
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARPS = 8;
@@ -31,13 +38,15 @@ constexpr int EPI_WARPS = 8;
 // memory write (TMA) and read (UMMA) traffic per SM drops by a third and L2->SM traffic by a third.
 template <int BN, int CTAS>
 struct GemmCfg {
-  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int A_SUB = BM * BKA * 2;             // one [128 x 64] sub-tile
+  static constexpr int A_BYTES = A_SUB * KSUB;
   static constexpr int B_ROWS = BN / CTAS;
-  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int B_SUB = B_ROWS * BKA * 2;
+  static constexpr int B_BYTES = B_SUB * KSUB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/;
-  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
+  static_assert(B_SUB % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
   static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
 };
 
@@ -56,6 +65,7 @@ struct EpiParams {
   int row_add_offset; // row_add row = (m % period) + offset
   int remap_stride;   // out row = (m / period) * remap_stride + remap_offset + (m % period)
   int remap_offset;
+  long long* dbg;     // optional per-CTA cycle counters (CGPT_GEMM_DBG): [grid][8]
 };
 
 // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16
@@ -239,11 +249,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -255,7 +265,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 2) {
+  if (warp == 10) {
     if (CTAS == 2) { tmem_alloc_2sm(tmem_ptr, 512); tmem_relinquish_2sm(); }
     else           { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
   }
@@ -265,7 +275,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -279,19 +289,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           if (CTAS == 2) {
             // the leader's barrier collects the bytes of BOTH CTAs' loads
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-            tma_load_2d_2sm(smem_b + stage * Cfg::B_BYTES, &tma_b, &full_bar[stage], kb * BK,
-                            n_blk * BN + cta_rank * Cfg::B_ROWS);
+#pragma unroll
+            for (int sub = 0; sub < KSUB; ++sub) {
+              tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES + sub * Cfg::A_SUB, &tma_a, &full_bar[stage],
+                              kb * BK + sub * BKA, m_blk * BM);
+              tma_load_2d_2sm(smem_b + stage * Cfg::B_BYTES + sub * Cfg::B_SUB, &tma_b, &full_bar[stage],
+                              kb * BK + sub * BKA, n_blk * BN + cta_rank * Cfg::B_ROWS);
+            }
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+#pragma unroll
+            for (int sub = 0; sub < KSUB; ++sub) {
+              tma_load_2d(smem_a + stage * Cfg::A_BYTES + sub * Cfg::A_SUB, &tma_a, &full_bar[stage],
+                          kb * BK + sub * BKA, m_blk * BM);
+              tma_load_2d(smem_b + stage * Cfg::B_BYTES + sub * Cfg::B_SUB, &tma_b, &full_bar[stage],
+                          kb * BK + sub * BKA, n_blk * BN);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM * CTAS, BN);
@@ -299,20 +318,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long t_wait_epi = 0, t_wait_tma = 0, t_total0 = clock64();
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        long long c0 = clock64();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        t_wait_epi += clock64() - c0;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kb = 0; kb < num_kb; ++kb) {
+          c0 = clock64();
           mbar_wait(&full_bar[stage], phase);
+          t_wait_tma += clock64() - c0;
           tcgen05_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in (addr >> 4) units
-            if (CTAS == 2) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            else           umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            // sub-tile (k / 4) of the stage, then 16 bf16 = 32 B inside the 128B swizzle atom (+2 in addr>>4 units)
+            const uint64_t ad = adesc + (k >> 2) * (Cfg::A_SUB >> 4) + 2 * (k & 3);
+            const uint64_t bd = bdesc + (k >> 2) * (Cfg::B_SUB >> 4) + 2 * (k & 3);
+            if (CTAS == 2) umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            else           umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
           }
           if (CTAS == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -320,28 +346,54 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         if (CTAS == 2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (epi.dbg) {
+        epi.dbg[blockIdx.x * 8 + 0] = t_wait_epi;
+        epi.dbg[blockIdx.x * 8 + 1] = t_wait_tma;
+        epi.dbg[blockIdx.x * 8 + 2] = clock64() - t_total0;
+      }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ------------------------------------------------------------ epilogue (8 warps)
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32)
-    const int half = (warp - 4) >> 2;      // column half of the tile
-    const int epi_tid = threadIdx.x - 128; // 0..255
+    const int half = warp >> 2;            // column half of the tile
+    const int epi_tid = threadIdx.x;       // 0..255
     constexpr int NCH = BN / 16;
     constexpr int NCH0 = (NCH + 1) / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long t_wait_mma = 0, t_work = 0, t_bar = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int m_blk, n_blk;
       tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
       m_blk = m_blk * CTAS + cta_rank;
       const int n_base = n_blk * BN;
       float* bias_s = bias_smem + acc * 256;
+      long long c0 = clock64();
       if (epi.bias != nullptr && epi_tid < BN) {
         const int n = n_base + epi_tid;
         bias_s[epi_tid] = n < N ? __ldg(epi.bias + n) : 0.f;
       }
+      {
+        // pull this thread's residual row segment towards L2 while the tile's MMAs still run: the
+        // row-per-thread residual loads below are latency-bound (25k cycles per tile vs 11k of MMA otherwise)
+        const int mp = m_blk * BM + quarter * 32 + lane;
+        if (epi.resid != nullptr && mp < M) {
+          long long orow = mp;
+          if (epi.row_period > 0 && epi.remap_stride > 0)
+            orow = (long long)(mp / epi.row_period) * epi.remap_stride + epi.remap_offset + (mp % epi.row_period);
+          const int c_lo = half == 0 ? 0 : NCH0 * 16, c_hi = half == 0 ? NCH0 * 16 : BN;
+          const int esz = epi.resid_f32 ? 4 : 2;
+          const char* rp = reinterpret_cast<const char*>(epi.resid) + (orow * epi.ldr + n_base) * esz;
+          for (int c = c_lo; c < c_hi && n_base + c < N; c += 128 / esz)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (long long)c * esz));
+        }
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
+      long long c1 = clock64();
+      t_bar += c1 - c0;
       mbar_wait(&tmem_full[acc], acc_phase);
+      c0 = clock64();
+      t_wait_mma += c0 - c1;
       tcgen05_fence_after();
       const int m = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = m < M;
@@ -355,7 +407,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
+      t_work += clock64() - c0;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (epi.dbg && threadIdx.x == 0) {
+      epi.dbg[blockIdx.x * 8 + 4] = t_wait_mma;
+      epi.dbg[blockIdx.x * 8 + 5] = t_work;
+      epi.dbg[blockIdx.x * 8 + 6] = t_bar;
     }
   }
 
@@ -363,7 +421,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   __syncwarp();
   __syncthreads();
   if (CTAS == 2) cluster_sync_all();   // peer smem / barriers stay valid until both CTAs are done
-  if (warp == 2) {
+  if (warp == 10) {
     tcgen05_fence_after();
     if (CTAS == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
@@ -394,7 +452,7 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
   CGPT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)BKA, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -471,6 +529,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   p.row_add = e->row_add; p.ld_row_add = e->ld_row_add;
   p.row_period = e->row_period; p.row_add_offset = e->row_add_offset;
   p.remap_stride = e->remap_stride; p.remap_offset = e->remap_offset;
+  p.dbg = reinterpret_cast<long long*>(getenv("CGPT_GEMM_DBG") ? strtoull(getenv("CGPT_GEMM_DBG"), nullptr, 0) : 0ull);
   CGPT_REQUIRE(p.row_add == nullptr || p.row_period > 0, "gemm: row_add needs row_period > 0");
   CGPT_REQUIRE(p.act != CGPT_ACT_SWIGLU || (!p.out_f32 && p.resid == nullptr && p.row_add == nullptr),
                "gemm: SwiGLU epilogue writes bf16 and takes no residual");

@@ -475,6 +475,50 @@ class MiniGPT4Engine:
         L.answer_labels(ids, self.table_keys, self.table_vals, self.other_label, self.cfg.llm.eos_id, out=labels)
         return labels
 
+    # ------------------------------------------------------------------ encoder-only path (BASELINE config #4)
+    def _encoder_buffers(self, B):
+        """Vision-side buffers only (no KV cache): lets the encoder sweep reach B = 4096."""
+        if getattr(self, "_enc_B", 0) >= B:
+            return self._enc_buf
+        cfg, dev = self.cfg, self.dev
+        v, q, l = cfg.vit, cfg.qf, cfg.llm
+        bf, f32 = torch.bfloat16, torch.float32
+        Mv, Mq = B * v.tokens, B * q.n_query
+        n_cross = len(q.cross_layers())
+
+        def e(*shape, dtype=bf):
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
+        self._enc_buf = None
+        torch.cuda.empty_cache()
+        self._enc_buf = {
+            "patches": e(B * v.grid * v.grid, 592),
+            "v.res": e(Mv, v.dim, dtype=f32), "v.xn": e(Mv, v.dim), "v.qkv": e(Mv, 3 * v.dim),
+            "v.att": e(Mv, v.dim), "v.h": e(Mv, v.mlp), "v.out": e(Mv, v.dim),
+            "q.h": e(Mq, q.hidden), "q.tmp": e(Mq, q.hidden, dtype=f32), "q.qkv": e(Mq, 3 * q.hidden),
+            "q.ctx": e(Mq, q.hidden), "q.cq": e(Mq, q.hidden), "q.ckv": e(Mv, n_cross * 2 * q.hidden),
+            "q.inter": e(Mq, q.inter), "enc.out": e(Mq, l.hidden),
+        }
+        self._enc_B = B
+        return self._enc_buf
+
+    @torch.no_grad()
+    def encode_noisy(self, x, B, sigma, *, seed=0, stream_id=0, first_sample=0,
+                     noise_space=L.SPACE_NORMALIZED, noise_kind=L.NOISE_GAUSSIAN,
+                     mean=L.BLIP_MEAN, std=L.BLIP_STD):
+        """MiniGPT4.encode_img (minigpt4.py:121-149) of B noisy copies of x: noise -> ViT-g -> ln_vision ->
+        Q-Former -> llama_proj; returns inputs_llama [B, n_query, llm.hidden] bf16."""
+        buf = self._encoder_buffers(B)
+        G2 = self.cfg.vit.grid ** 2
+        L.noise_patchify(x, B, sigma, seed=seed, stream_id=stream_id, first_sample=first_sample,
+                         noise_space=noise_space, noise_kind=noise_kind, mean=mean, std=std,
+                         out=buf["patches"][:B * G2])
+        img = self.vit_from_patches(B, buf)
+        qo = self.qformer(B, buf, img)
+        out = buf["enc.out"][:B * self.cfg.qf.n_query]
+        L.gemm(qo, self.w["proj.w"], bias=self.w["proj.b"], out=out)
+        return out.view(B, self.cfg.qf.n_query, -1)
+
     @torch.no_grad()
     def forward_images(self, images, collect=None):
         """Deterministic forward of an image batch [B,3,S,S] (already in model input space);
