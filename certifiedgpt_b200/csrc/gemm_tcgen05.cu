@@ -65,6 +65,7 @@ struct EpiParams {
   int row_add_offset; // row_add row = (m % period) + offset
   int remap_stride;   // out row = (m / period) * remap_stride + remap_offset + (m % period)
   int remap_offset;
+  int red_inplace;    // out aliases the fp32 residual: accumulate with red.global.add (no residual load)
   long long* dbg;     // optional per-CTA cycle counters (CGPT_GEMM_DBG): [grid][8]
 };
 
@@ -145,6 +146,18 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
     *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
     return;
   }
+  if (p.red_inplace) {
+    // in-place fp32 residual update (x += proj(...)): every element is touched by exactly one thread, so an
+    // uncontended fire-and-forget L2 reduction replaces the latency-bound load + add + store (same single
+    // fp32 addition, bit-identical result)
+    float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
+#pragma unroll
+    for (int i = 0; i < NC; i += 4)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(v[i]), "f"(v[i + 1]),
+                   "f"(v[i + 2]), "f"(v[i + 3])
+                   : "memory");
+    return;
+  }
   if (p.row_add != nullptr) {
     const float* ra = p.row_add + (long long)((m % p.row_period) + p.row_add_offset) * p.ld_row_add + n0;
 #pragma unroll
@@ -181,7 +194,7 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams&
                                                 int c0, int c1) {
   uint32_t r0[16], r1[16];
   float rr0[16], rr1[16];
-  const bool has_res = epi.resid != nullptr && row_ok;
+  const bool has_res = epi.resid != nullptr && row_ok && !epi.red_inplace;
   tmem_ld_x16(t_row + c0 * 16, r0);
   if (has_res && n_base + c0 * 16 < N) load_resid16(epi, out_row, n_base + c0 * 16, rr0);
 #pragma unroll 1
@@ -377,7 +390,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         // pull this thread's residual row segment towards L2 while the tile's MMAs still run: the
         // row-per-thread residual loads below are latency-bound (25k cycles per tile vs 11k of MMA otherwise)
         const int mp = m_blk * BM + quarter * 32 + lane;
-        if (epi.resid != nullptr && mp < M) {
+        if (epi.resid != nullptr && !epi.red_inplace && mp < M) {
           long long orow = mp;
           if (epi.row_period > 0 && epi.remap_stride > 0)
             orow = (long long)(mp / epi.row_period) * epi.remap_stride + epi.remap_offset + (mp % epi.row_period);
@@ -529,6 +542,8 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   p.row_add = e->row_add; p.ld_row_add = e->ld_row_add;
   p.row_period = e->row_period; p.row_add_offset = e->row_add_offset;
   p.remap_stride = e->remap_stride; p.remap_offset = e->remap_offset;
+  p.red_inplace = (p.resid != nullptr && p.resid == p.out && p.out_f32 && p.resid_f32 && p.ldr == p.ldo &&
+                   p.act == CGPT_ACT_NONE && p.row_add == nullptr && !getenv("CGPT_GEMM_NO_RED")) ? 1 : 0;
   p.dbg = reinterpret_cast<long long*>(getenv("CGPT_GEMM_DBG") ? strtoull(getenv("CGPT_GEMM_DBG"), nullptr, 0) : 0ull);
   CGPT_REQUIRE(p.row_add == nullptr || p.row_period > 0, "gemm: row_add needs row_period > 0");
   CGPT_REQUIRE(p.act != CGPT_ACT_SWIGLU || (!p.out_f32 && p.resid == nullptr && p.row_add == nullptr),
