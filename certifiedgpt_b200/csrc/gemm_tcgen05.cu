@@ -143,7 +143,7 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
 #pragma unroll
     for (int i = 0; i < NC / 4; ++i)
       w[i] = pack_bf16x2(silu_fast(v[4 * i]) * v[4 * i + 1], silu_fast(v[4 * i + 2]) * v[4 * i + 3]);
-    *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    __stcs(reinterpret_cast<uint4*>(o), make_uint4(w[0], w[1], w[2], w[3]));
     return;
   }
   if (p.red_inplace) {
@@ -174,14 +174,16 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
     float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
 #pragma unroll
     for (int i = 0; i < NC; i += 4)
-      *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      __stcs(reinterpret_cast<float4*>(o + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
   } else {
+    // streaming (evict-first) stores: the output is consumed by the NEXT kernel after GBs of other traffic,
+    // so it should not push this GEMM's re-used A band out of L2
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n0;
 #pragma unroll
     for (int i = 0; i < NC; i += 8)
-      *reinterpret_cast<uint4*>(o + i) =
-          make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
-                     pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+      __stcs(reinterpret_cast<uint4*>(o + i),
+             make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                        pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7])));
   }
 }
 
