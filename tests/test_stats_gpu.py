@@ -113,3 +113,20 @@ def test_answer_labels(lib):
                         [6, 5, 2, 0], [2, 5, 6, 0], [31999, 4, 9, 2]], dtype=torch.int32, device="cuda")
     lab = lib.answer_labels(ids, keys, vals, other_label=4)
     assert lab.cpu().tolist() == [0, 1, 2, 4, 0, 4, 4, 3]
+
+
+def test_answer_vocabulary_to_device_labels(lib):
+    """text vocabulary -> token-sequence table -> device hash lookup agrees with the text-level normaliser."""
+    from certifiedgpt_b200.answers import AnswerVocabulary
+    vocab = AnswerVocabulary(["yes", "no", "2", "red car"])
+    enc = lambda s: [3 + (ord(c) % 90) for c in s]           # toy tokenizer
+    keys, vals = lib.build_answer_table(vocab.table_entries(enc))
+    gen = ["yes", " Yes", "No.", "red car", "purple", " 2", "Red Car"]
+    width = max(len(enc(g)) for g in gen) + 2
+    rows = []
+    for g in gen:
+        ids = enc(g) + [2]                                    # EOS terminates the answer
+        rows.append(ids + [0] * (width - len(ids)))
+    ids = torch.tensor(rows, dtype=torch.int32, device="cuda")
+    lab = lib.answer_labels(ids, keys, vals, other_label=vocab.other).cpu().tolist()
+    assert lab == [vocab.label_of_text(g) for g in gen]
