@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--cpu-samples", type=int, default=2, help="bounded CPU-baseline sample (noisy samples)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="tiny model (debug only; not a bench number)")
+    ap.add_argument("--engine", default="native", choices=["native", "python"],
+                    help="native: the whole loop inside libcgpt (cgpt_certify); python: engine.py drives the kernels")
     return ap.parse_args()
 
 
@@ -201,6 +203,7 @@ def run_ours(args, cfg):
     import torch.distributed as dist
     from certifiedgpt_b200 import _lib as L
     from certifiedgpt_b200.engine import MiniGPT4Engine
+    from certifiedgpt_b200.native import NativeMiniGPT4Engine
     from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
     from certifiedgpt_b200.weights import random_state_dict
 
@@ -216,8 +219,9 @@ def run_ours(args, cfg):
 
     sd = random_state_dict(cfg, seed=0, device=dev)
     prefix, suffix = prompt_ids(cfg.llm.vocab)
-    eng = MiniGPT4Engine(cfg, sd, prefix, suffix, answer_table(cfg.llm.vocab, NUM_CLASSES), NUM_CLASSES,
-                         max_new_tokens=args.max_new_tokens, device=dev, early_exit=True)
+    Engine = NativeMiniGPT4Engine if args.engine == "native" else MiniGPT4Engine
+    eng = Engine(cfg, sd, prefix, suffix, answer_table(cfg.llm.vocab, NUM_CLASSES), NUM_CLASSES,
+                 max_new_tokens=args.max_new_tokens, device=dev, early_exit=True)
     del sd
     torch.cuda.empty_cache()
     smooth = Smooth(eng, NUM_CLASSES, SIGMA, seed=42, process_group=True if world > 1 else None)
@@ -249,25 +253,38 @@ def run_ours(args, cfg):
     x_stage = torch.empty_like(x_dev)
 
     def step_e2e():
+        if args.engine == "native":
+            # HOST buffers straight through the C-ABI: cgpt_certify stages x (H2D from pinned memory) and reads
+            # back (label, radius, cAHat, pABar, nA) - both copies inside the timed region
+            return smooth.certify(x_host, args.n0, args.n, ALPHA, args.batch_size)
         x_stage.copy_(x_host, non_blocking=True)          # H2D of the step's input from pinned memory
         return smooth.certify(x_stage, args.n0, args.n, ALPHA, args.batch_size)   # D2H of (label, radius)
 
     for _ in range(args.warmup):
         step_resident()
-    launches0 = L.launch_count() + eng.replayed_launches
+    def n_launches():   # libcgpt counts eager launches and replayed graph nodes; the python engine counts its replays
+        return L.launch_count() + getattr(eng, "replayed_launches", 0)
+
+    launches0 = n_launches()
     with ClockSampler(local) as clocks:
         ms = timed(step_resident, args.steps)
-    launches = L.launch_count() + eng.replayed_launches - launches0
+    launches = n_launches() - launches0
     ms_e2e = timed(step_e2e, args.steps)
     result = step_resident()
     # roofline pass: the same steps launched eagerly (not as graph replays) so that every GEMM launch can be
     # bracketed by a CUDA-event pair on its stream; same kernels, same shapes, same data
-    eng.use_graphs = False
+    def set_graphs(on):
+        if args.engine == "native":
+            eng.set_option("use_graphs", on)
+        else:
+            eng.use_graphs = on
+
+    set_graphs(False)
     step_resident()
     L.gemm_profile_start()
     ms_prof = timed(step_resident, args.steps)
     prof = L.gemm_profile_stop()
-    eng.use_graphs = True
+    set_graphs(True)
 
     value = per_step * args.steps / (ms / 1e3)
     e2e = per_step * args.steps / (ms_e2e / 1e3)
@@ -309,7 +326,10 @@ def run_ours(args, cfg):
             "data": "synthetic", "config": workload_config(args, cfg, world),
             "certified_images_per_min": value * 60.0 / per_step,
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": 24, "certified_images_per_min": e2e * 60.0 / per_step},
+                    "d2h_bytes_per_step": 32 if args.engine == "native" else 24,
+                    "certified_images_per_min": e2e * 60.0 / per_step,
+                    "api": ("Smooth.certify(x_host) -> cgpt_certify (C-ABI, host x, host label/radius)"
+                            if args.engine == "native" else "Smooth.certify(x_dev) after an explicit pinned H2D copy")},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the timed steps)",
@@ -321,6 +341,7 @@ def run_ours(args, cfg):
                          "top_shapes": {k: {"ms": round(v[0], 3), "tflops": round(v[1] / (v[0] / 1e3) / 1e12, 1), "launches": v[2]}
                                         for k, v in top}},
             "result": {"label": result[0], "radius": result[1], "decode_steps": eng.last_steps},
+            "engine": args.engine,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -101,6 +101,8 @@ def _EXTRA_SIGS(vp, i64, i32, f32, f64, u64):
         "cgpt_attention": [C.POINTER(AttnArgs), vp],
         "cgpt_rope_split": [vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, i32, i32, vp],
         "cgpt_gather_rows": [vp, i64, vp, i32, i32, i32, vp, i64, i32, i32, i32, i32, vp],
+        "cgpt_gemm_profile_begin": [],
+        "cgpt_gemm_profile_end": [vp, vp, i32, C.POINTER(C.c_int)],
     }
 
 
@@ -126,21 +128,24 @@ def launch_count():
 
 
 # ------------------------------------------------------------------------------- GEMM
-_gemm_prof = None
-
-
 def gemm_profile_start():
-    """Record a CUDA-event pair around every GEMM launch (bench.py roofline measurement)."""
-    global _gemm_prof
-    _gemm_prof = []
+    """Bracket every eager GEMM launch (cgpt_gemm_bf16 and the native engine's) with a CUDA-event pair on its
+    stream, inside libcgpt (bench.py roofline measurement)."""
+    check(load().cgpt_gemm_profile_begin())
 
 
 def gemm_profile_stop():
     """-> list of (ms, flops, (M, N, K)); synchronises."""
-    global _gemm_prof
-    rec, _gemm_prof = _gemm_prof or [], None
-    torch.cuda.synchronize()
-    return [(s.elapsed_time(e), fl, shp) for s, e, fl, shp in rec]
+    import numpy as np
+    cap = 1 << 16
+    ms = np.zeros(cap, dtype=np.float32)
+    mnk = np.zeros(3 * cap, dtype=np.int32)
+    n = C.c_int(0)
+    check(load().cgpt_gemm_profile_end(ms.ctypes.data_as(C.c_void_p), mnk.ctypes.data_as(C.c_void_p), cap,
+                                       C.byref(n)))
+    k = min(n.value, cap)
+    return [(float(ms[i]), 2.0 * float(mnk[3 * i]) * float(mnk[3 * i + 1]) * float(mnk[3 * i + 2]),
+             (int(mnk[3 * i]), int(mnk[3 * i + 1]), int(mnk[3 * i + 2]))) for i in range(k)]
 
 
 def gemm(a, w, *, out=None, bias=None, resid=None, act=ACT_NONE, out_dtype=torch.bfloat16,
@@ -173,14 +178,8 @@ def gemm(a, w, *, out=None, bias=None, resid=None, act=ACT_NONE, out_dtype=torch
     e.row_period = row_period; e.row_add_offset = row_add_offset
     e.remap_stride = remap_stride; e.remap_offset = remap_offset
     e.max_ctas = max_ctas
-    if _gemm_prof is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
     check(lib.cgpt_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K,
                              C.byref(e), force_bn, stream_ptr()))
-    if _gemm_prof is not None:
-        ev1.record()
-        _gemm_prof.append((ev0, ev1, 2.0 * M * N * K, (M, N, K)))
     return out
 
 

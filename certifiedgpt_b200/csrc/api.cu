@@ -14,6 +14,7 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+long long total_launch_count() { return g_launches + gemm_launch_count(); }
 }  // namespace cgpt
 
 using namespace cgpt;
@@ -23,6 +24,11 @@ extern "C" {
 const char* cgpt_last_error(void) { return g_err; }
 int cgpt_abi_version(void) { return CGPT_ABI_VERSION; }
 long long cgpt_launch_count(void) { return g_launches + gemm_launch_count(); }
+
+int cgpt_gemm_profile_begin(void) { return gemm_profile_begin(); }
+int cgpt_gemm_profile_end(float* ms_out, int32_t* mnk_out, int capacity, int* count) {
+  return gemm_profile_end(ms_out, mnk_out, capacity, count);
+}
 
 int cgpt_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                    const cgpt_gemm_epilogue* epi, int force_bn, void* stream) {

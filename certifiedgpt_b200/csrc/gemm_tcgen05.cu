@@ -20,6 +20,7 @@
 //                                (prefetched) / pos-embed -> bf16 or fp32 global stores, overlapped
 //                                with the next tile's MMAs through the second TMEM stage
 #include <stdlib.h>
+#include <deque>
 #include "common.cuh"
 #include "ops.h"
 
@@ -480,6 +481,10 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
 static int g_num_sms = 0;
 static int g_gemm_launches = 0;
 
+struct GemmProfRec { cudaEvent_t e0, e1; int M, N, K; };
+static std::deque<GemmProfRec> g_prof;
+static bool g_prof_on = false;
+
 template <int BN, int CTAS>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                        const EpiParams& epi, int max_ctas, cudaStream_t stream) {
@@ -562,15 +567,59 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, A, M, K, lda, BM)) return rc;
   if (int rc = make_tmap(&tb, W, N, K, ldw, bn / ctas)) return rc;
+  // timing hook: only outside stream capture (events cannot bracket a graph node)
+  GemmProfRec* rec = nullptr;
+  if (g_prof_on) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+      g_prof.push_back(GemmProfRec{nullptr, nullptr, M, N, K});
+      rec = &g_prof.back();
+      CGPT_CHECK_CUDA(cudaEventCreate(&rec->e0));
+      CGPT_CHECK_CUDA(cudaEventCreate(&rec->e1));
+      CGPT_CHECK_CUDA(cudaEventRecord(rec->e0, stream));
+    }
+  }
+  int rc = 0;
   switch (bn * 10 + ctas) {
-    case 2561: return launch_gemm<256, 1>(ta, tb, M, N, K, p, e->max_ctas, stream);
-    case 1761: return launch_gemm<176, 1>(ta, tb, M, N, K, p, e->max_ctas, stream);
-    case 1281: return launch_gemm<128, 1>(ta, tb, M, N, K, p, e->max_ctas, stream);
-    case 2562: return launch_gemm<256, 2>(ta, tb, M, N, K, p, e->max_ctas, stream);
-    case 1762: return launch_gemm<176, 2>(ta, tb, M, N, K, p, e->max_ctas, stream);
-    case 1282: return launch_gemm<128, 2>(ta, tb, M, N, K, p, e->max_ctas, stream);
+    case 2561: rc = launch_gemm<256, 1>(ta, tb, M, N, K, p, e->max_ctas, stream); break;
+    case 1761: rc = launch_gemm<176, 1>(ta, tb, M, N, K, p, e->max_ctas, stream); break;
+    case 1281: rc = launch_gemm<128, 1>(ta, tb, M, N, K, p, e->max_ctas, stream); break;
+    case 2562: rc = launch_gemm<256, 2>(ta, tb, M, N, K, p, e->max_ctas, stream); break;
+    case 1762: rc = launch_gemm<176, 2>(ta, tb, M, N, K, p, e->max_ctas, stream); break;
+    case 1282: rc = launch_gemm<128, 2>(ta, tb, M, N, K, p, e->max_ctas, stream); break;
     default: CGPT_REQUIRE(false, "gemm: unsupported N tile %d", bn);
   }
+  if (rec != nullptr && rc == 0) CGPT_CHECK_CUDA(cudaEventRecord(rec->e1, stream));
+  return rc;
+}
+
+int gemm_profile_begin() {
+  for (auto& r : g_prof) {
+    if (r.e0) cudaEventDestroy(r.e0);
+    if (r.e1) cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  g_prof_on = true;
+  return 0;
+}
+
+int gemm_profile_end(float* ms_out, int* mnk_out, int capacity, int* count) {
+  g_prof_on = false;
+  CGPT_CHECK_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  for (auto& r : g_prof) {
+    if (n < capacity && ms_out != nullptr && mnk_out != nullptr) {
+      float ms = 0.f;
+      CGPT_CHECK_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+      ms_out[n] = ms;
+      mnk_out[3 * n] = r.M; mnk_out[3 * n + 1] = r.N; mnk_out[3 * n + 2] = r.K;
+    }
+    ++n;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  if (count != nullptr) *count = n;
   return 0;
 }
 

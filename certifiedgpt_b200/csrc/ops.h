@@ -10,6 +10,9 @@ void count_launch(int n = 1);
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
               const cgpt_gemm_epilogue* e, int force_bn, cudaStream_t stream);
 int gemm_launch_count();
+int gemm_profile_begin();
+int gemm_profile_end(float* ms_out, int* mnk_out, int capacity, int* count);
+long long total_launch_count();
 
 int noise_patchify(const float* x, const float* eps, uint64_t seed, uint32_t stream_id,
                    uint64_t first_sample, int B, float sigma, const float* mean3,

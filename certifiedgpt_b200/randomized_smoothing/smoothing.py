@@ -71,6 +71,17 @@ class Smooth(object):
         """Monte Carlo certification (smoothing.py:29-56).  Returns (class, radius) or (ABSTAIN, 0.0)."""
         self._eval()
         self._cursor = 0
+        if self._native() and self.fuse_selection and not callable(self._injected):
+            # whole call inside libcgpt (cgpt_certify): fused selection+estimation pass, device tail, one D2H read;
+            # x may live on the host (the library stages it) or on the device
+            label, radius, d = self.base_classifier.certify(
+                self._as_f32(x), n0, n, alpha, batch_size, self.sigma, eps=self._injected, process_group=self.process_group,
+                **self._noise_kw())
+            self.last_cAHat, self.last_pABar = d["cAHat"], d["pABar"]
+            self.last_counts_selection, self.last_counts_estimation = d["counts_selection"], d["counts_estimation"]
+            self.last_counts = self.last_counts_selection
+            self.image_id += 1
+            return (Smooth.ABSTAIN, 0.0) if label == Smooth.ABSTAIN else (label, radius)
         if self.fuse_selection:
             # The n0 selection draws and the n estimation draws are independent (fresh noise, smoothing.py:44,48)
             # and keyed by global sample index, so both phases run as ONE sharded pass over [0, n0 + n) and are
@@ -95,6 +106,12 @@ class Smooth(object):
         """Monte Carlo prediction with the top-2 binomial test (smoothing.py:58-79)."""
         self._eval()
         self._cursor = 0
+        if self._native() and not callable(self._injected):
+            label, self.last_pvalue, self.last_counts = self.base_classifier.predict(
+                self._as_f32(x), n, alpha, batch_size, self.sigma, eps=self._injected, process_group=self.process_group,
+                **self._noise_kw())
+            self.image_id += 1
+            return label
         counts = self._sample_noise_device(x, n, batch_size)
         lab, st = L.predict_tail(counts, alpha)
         label = int(lab[0].item())
@@ -122,6 +139,17 @@ class Smooth(object):
         return float(st[1].item())
 
     # ------------------------------------------------------------------ device loop
+    def _native(self):
+        return bool(getattr(self.base_classifier, "cgpt_native", False))
+
+    @staticmethod
+    def _as_f32(x):
+        return x.detach().to(torch.float32).contiguous()
+
+    def _noise_kw(self):
+        return dict(seed=self.seed, stream_id=self.image_id, noise_space=self.noise_space,
+                    noise_kind=self.noise_kind, mean=self.mean, std=self.std)
+
     def _eval(self):
         ev = getattr(self.base_classifier, "eval", None)
         if callable(ev):
@@ -140,6 +168,15 @@ class Smooth(object):
     def _sample_noise_device(self, x, num: int, batch_size, split=None):
         """Counts over the global sample range [cursor, cursor + num).  With `split`, samples
         [cursor, cursor + split) are counted into a first vector and the rest into a second one."""
+        if self._native() and not callable(self._injected):
+            # the whole Monte-Carlo loop (chunking, sharding, histogram, NCCL all-reduce) runs inside libcgpt
+            counts2 = self.base_classifier.sample_noise(
+                self._as_f32(x), num, batch_size, self.sigma, base=self._cursor, split=split, eps=self._injected,
+                process_group=self.process_group, **self._noise_kw())
+            self._cursor += num
+            self.last_counts = counts2[0]
+            self.last_invalid = self.base_classifier.last_invalid
+            return counts2[0] if split is None else (counts2[0], counts2[1])
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
             raise L.CgptError("Smooth: x must be a CUDA tensor (no CPU path exists)")
         x = x.detach().to(torch.float32).contiguous()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CGPT_ABI_VERSION 1
+#define CGPT_ABI_VERSION 2
 
 enum { CGPT_DT_BF16 = 0, CGPT_DT_F32 = 1 };
 enum { CGPT_ACT_NONE = 0, CGPT_ACT_GELU = 1, CGPT_ACT_SWIGLU = 2 };
@@ -166,6 +166,120 @@ int cgpt_rope_split(void* qkv, int64_t ld, int rows, int T, int H, int head_dim,
 int cgpt_gather_rows(const void* table, int64_t ldt, const int32_t* ids, int id_period, int rows, int D,
                      void* out, int64_t ldo, int out_dtype, int remap_period, int remap_stride,
                      int remap_offset, void* stream);
+
+
+/* ---------------------------------------------------------------- GEMM timing hook (bench.py roofline)
+ * begin: from now on every cgpt_gemm_bf16 / engine GEMM launch (eager launches only, not graph replays) is
+ * bracketed by a CUDA-event pair on its stream.  end: synchronises, writes up to `capacity` records
+ * (ms_out[i], mnk_out[3*i..3*i+2] = M,N,K) and the total number of records to *count, stops recording. */
+int cgpt_gemm_profile_begin(void);
+int cgpt_gemm_profile_end(float* ms_out, int32_t* mnk_out, int capacity, int* count);
+
+/* ================================================================= native engine
+ * The whole MiniGPT-4 noisy-sample classifier behind one handle: host-side
+ * C++ orchestration of the kernels above, CUDA-graph replay per batch size, no Python in the loop.
+ *   cgpt_create -> cgpt_bind_weight (x every packed tensor) -> cgpt_set_prompt -> cgpt_set_answer_table
+ *   -> cgpt_workspace_bytes / cgpt_bind_workspace (caller-owned device memory; the library allocates
+ *   nothing on the device) -> cgpt_sample_noise / cgpt_certify / cgpt_predict, or the per-subsystem
+ *   entry points cgpt_vit_forward / cgpt_qformer_forward / cgpt_llm_prefill_decode.
+ * Replaces: Smooth._sample_noise / certify / predict (randomized_smoothing/smoothing.py:29-117),
+ * MiniGPT4.encode_img (minigpt4.py:121-149) and MiniGPTBase.generate (minigpt_base.py:374-448). */
+typedef struct cgpt_model_config {
+  /* EVA ViT (eva_vit.py:425-437) */
+  int img_size, vit_dim, vit_depth, vit_heads, vit_mlp;
+  float vit_eps, ln_vision_eps;
+  /* Q-Former (minigpt4.py:90-119) */
+  int qf_hidden, qf_layers, qf_heads, qf_inter, qf_queries, qf_cross_freq;
+  float qf_eps;
+  /* Llama (HF LlamaConfig) */
+  int llm_hidden, llm_layers, llm_heads, llm_inter, llm_vocab;
+  float llm_rms_eps;
+  int eos_id, pad_id;
+  /* generation + adapter (minigpt_base.py:374-448) */
+  int n_prefix, n_suffix;          /* prompt token counts before the image / after it        */
+  int max_new_tokens, min_length;
+  int num_classes;                 /* unknown answers map to num_classes - 1 ("other")       */
+  int early_exit;                  /* 1: stop decoding when every row has emitted EOS (HF)   */
+  int use_graphs;                  /* 1: CUDA-graph replay of the per-batch kernel sequence  */
+} cgpt_model_config;
+
+typedef struct cgpt_engine* cgpt_handle;
+
+/* how the noise of one certify/predict call is drawn (smoothing.py:95-97; see cgpt_noise_patchify) */
+typedef struct cgpt_noise_spec {
+  uint64_t seed;
+  uint32_t stream_id;              /* image id (Philox key)                                   */
+  float sigma;
+  float mean[3], std[3];           /* BLIP Normalize constants (used when noise_space = PIXEL) */
+  int noise_space, noise_kind;
+  const float* eps;                /* NULL = Philox; else injected standard draws for global sample 0, 1, ...
+                                      ([n_total, 3, S, S] fp32, device) */
+} cgpt_noise_spec;
+
+int cgpt_create(const cgpt_model_config* cfg, cgpt_handle* out);
+int cgpt_destroy(cgpt_handle h);
+/* Binds one packed tensor by name (device pointer, caller keeps it alive).  bf16 matrices are K-major
+ * [out, in] (nn.Linear layout); names and packing: certifiedgpt_b200/engine.py::_pack. */
+int cgpt_bind_weight(cgpt_handle h, const char* name, const void* ptr, int64_t rows, int64_t cols, int dtype);
+/* prompt token ids around the image (minigpt_base.py:75-89): device int32 arrays of n_prefix / n_suffix ids */
+int cgpt_set_prompt(cgpt_handle h, const int32_t* prefix_ids, const int32_t* suffix_ids);
+int cgpt_set_answer_table(cgpt_handle h, const uint64_t* table_keys, const int32_t* table_vals, int capacity);
+/* device bytes needed for batches of up to max_batch samples (encoder_only != 0: no LLM buffers / KV cache) */
+int cgpt_workspace_bytes(cgpt_handle h, int max_batch, int encoder_only, int64_t* bytes);
+/* carves the workspace, computes the shared prompt-prefix K/V once and replicates it into the KV cache */
+int cgpt_bind_workspace(cgpt_handle h, void* workspace, int64_t bytes, int max_batch, int encoder_only,
+                        void* stream);
+
+/* (2) EVA ViT-g + ln_vision: patches bf16 [B*G*G, 592] -> image tokens bf16 [B*T, vit_dim] */
+int cgpt_vit_forward(cgpt_handle h, const void* patches, int B, void* out_tokens, void* stream);
+/* (2) Q-Former (+ optional llama_proj): tokens bf16 [B*T, vit_dim] -> queries bf16 [B*32, qf_hidden];
+ * out_llm_embeds (nullable) receives llama_proj(queries) bf16 [B*32, llm_hidden] (encode_img's inputs_llama) */
+int cgpt_qformer_forward(cgpt_handle h, const void* tokens, int B, void* out_queries, void* out_llm_embeds,
+                         void* stream);
+/* (3) llama_proj + prompt assembly + prefill over the shared prefix KV + greedy decode:
+ * queries bf16 [B*32, qf_hidden] -> out_ids int32 [B, max_new_tokens], out_top2_margin f32 [B, max_new_tokens]
+ * (nullable), *out_steps (host, nullable) = decode steps actually run.  Synchronises the stream between
+ * steps only when early_exit is set. */
+int cgpt_llm_prefill_decode(cgpt_handle h, const void* queries, int B, int32_t* out_ids, float* out_top2_margin,
+                            int* out_steps, void* stream);
+/* one batch of the hot loop: labels[b] = class of f(x + sigma * eps_{first_sample + b}), b < B.
+ * x: fp32 [3,S,S] device pointer.  labels: device int32 [B]. */
+int cgpt_noisy_labels(cgpt_handle h, const float* x, const cgpt_noise_spec* noise, uint64_t first_sample, int B,
+                      int32_t* labels, void* stream);
+/* Smooth._sample_noise (smoothing.py:81-99) over the global sample range [base, base+num), this rank's
+ * contiguous slice of it when world > 1.  counts: device int64 [nvec * num_classes], zeroed here; with
+ * split >= 0 samples [base, base+split) are counted into vector 0 and the rest into vector 1 (nvec = 2).
+ * x may be a host or a device pointer.  comm (nullable): all-reduces the counts (cgpt_comm_init).
+ * No host synchronisation unless early_exit is set. */
+int cgpt_sample_noise(cgpt_handle h, const float* x, const cgpt_noise_spec* noise, int64_t base, int64_t num,
+                      int batch_size, int64_t split, int rank, int world, void* comm, int64_t* counts,
+                      int32_t* invalid, void* stream);
+/* Smooth.certify (smoothing.py:29-56): one fused pass over [0, n0+n), device tail, one D2H read.
+ * x: host or device fp32 [3,S,S].  out_label (host): class or -1 (ABSTAIN); out_radius (host);
+ * out_detail (host, nullable) double[3] = {cAHat, pABar, nA}. */
+int cgpt_certify(cgpt_handle h, const float* x, const cgpt_noise_spec* noise, int64_t n0, int64_t n, double alpha,
+                 int batch_size, int rank, int world, void* comm, int* out_label, double* out_radius,
+                 double* out_detail, void* stream);
+/* Smooth.predict (smoothing.py:58-79); out_detail (host, nullable) double[1] = {p-value} */
+int cgpt_predict(cgpt_handle h, const float* x, const cgpt_noise_spec* noise, int64_t n, double alpha,
+                 int batch_size, int rank, int world, void* comm, int* out_label, double* out_detail,
+                 void* stream);
+/* device count vectors of the last cgpt_certify / cgpt_predict (int64 [2 * num_classes]; diagnostics) */
+int cgpt_last_counts(cgpt_handle h, const int64_t** counts);
+/* decode steps run by the last batch (< max_new_tokens when early_exit stopped the loop), or -1 */
+int cgpt_last_decode_steps(cgpt_handle h);
+/* run-time switches: "use_graphs" (0 = launch every kernel eagerly, e.g. for per-kernel timing),
+ * "early_exit" */
+int cgpt_set_option(cgpt_handle h, const char* key, int value);
+
+/* ---------------------------------------------------------------- the one collective on the path
+ * int64 label-count all-reduce over NCCL (NVLink / NVSwitch).  The communicator is created from a
+ * 128-byte ncclUniqueId that rank 0 obtains and the caller broadcasts (e.g. torch.distributed).
+ * libnccl.so.2 is resolved at run time (dlopen); without it these calls fail. */
+int cgpt_comm_unique_id(void* id128);
+int cgpt_comm_init(const void* id128, int rank, int world, void** comm);
+int cgpt_comm_destroy(void* comm);
+int cgpt_allreduce_counts(int64_t* counts, int n, void* comm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,11 @@ def _declared_symbols():
 def test_header_declares_the_hot_path_entry_points():
     names = _declared_symbols()
     for must in ["cgpt_noise_patchify", "cgpt_gemm_bf16", "cgpt_label_hist", "cgpt_certify_tail",
-                 "cgpt_predict_tail", "cgpt_answer_labels", "cgpt_last_error"]:
+                 "cgpt_predict_tail", "cgpt_answer_labels", "cgpt_last_error",
+                 # the per-subsystem entry points SURVEY.md 8(b) lists
+                 "cgpt_create", "cgpt_destroy", "cgpt_bind_weight", "cgpt_workspace_bytes", "cgpt_vit_forward",
+                 "cgpt_qformer_forward", "cgpt_llm_prefill_decode", "cgpt_sample_noise", "cgpt_certify",
+                 "cgpt_predict", "cgpt_allreduce_counts"]:
         assert must in names
 
 
@@ -28,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in _declared_symbols() if not hasattr(lib, n)]
     assert not missing, f"libcgpt.so lacks {missing}"
     lib.cgpt_abi_version.restype = ctypes.c_int
-    assert lib.cgpt_abi_version() == 1
+    assert lib.cgpt_abi_version() == 2
 
 
 def test_no_cpu_fallback_for_compute():
@@ -47,3 +51,43 @@ def test_answer_hash_canonicalisation_host():
     assert L.answer_hash([5, 6, 2, 9]) == L.answer_hash([0, 5, 1, 6]) == L.answer_hash([5, 6])
     assert L.answer_hash([5, 6]) != L.answer_hash([6, 5])
     assert L.answer_hash([5]) != L.answer_hash([5, 5])
+
+
+def test_native_engine_structs_match_the_header():
+    """ctypes mirrors of cgpt_model_config / cgpt_noise_spec: one field per header field, same order."""
+    from certifiedgpt_b200 import native as N
+    src = open(os.path.join(ROOT, "include", "cgpt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+
+    def fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), src, flags=re.S).group(1)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(None, 1)[1] if not decl.startswith("const") else decl.split("*")[1]
+            out += [re.sub(r"\[.*?\]", "", n).strip().lstrip("*") for n in names.split(",")]
+        return out
+
+    assert fields("cgpt_model_config") == [f[0] for f in N.ModelConfigC._fields_]
+    assert fields("cgpt_noise_spec") == [f[0] for f in N.NoiseSpecC._fields_]
+    assert ctypes.sizeof(N.ModelConfigC) == 4 * len(N.ModelConfigC._fields_)
+    assert ctypes.sizeof(N.NoiseSpecC) == 56
+
+
+def test_native_engine_refuses_to_start_without_a_gpu():
+    """cgpt_create needs a CUDA context (stream + pinned scratch): on a CPU-only host it must fail with a
+    message, never hand out a handle that would compute elsewhere."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from certifiedgpt_b200 import native as N
+    from certifiedgpt_b200.config import ModelConfig
+    h = N.lib()
+    c = N.config_struct(ModelConfig.tiny(), 3, 4, 2, 1, 6, True, True)
+    hd = ctypes.c_void_p()
+    rc = h.cgpt_create(ctypes.byref(c), ctypes.byref(hd))
+    assert rc != 0 and not hd.value and len(h.cgpt_last_error()) > 0
+    bad = N.config_struct(ModelConfig.tiny(), 3, 4, 0, 1, 6, True, True)    # max_new_tokens = 0
+    assert h.cgpt_create(ctypes.byref(bad), ctypes.byref(hd)) == -1

@@ -1,0 +1,225 @@
+"""GPU tests of libcgpt's native engine (cgpt_create ... cgpt_certify, include/cgpt.h):
+
+* the C++ orchestration launches the same kernels in the same order as the Python twin (engine.py), so
+  token ids, labels and counts must be BIT-IDENTICAL to it (eager and CUDA-graph replay);
+* the per-subsystem entry points (cgpt_vit_forward / cgpt_qformer_forward / cgpt_llm_prefill_decode)
+  match the fp32 oracle within bf16 tolerance (rel 2e-2) and the Python twin bit for bit;
+* Smooth over the native engine equals the oracle on identical injected noise (counts exact wherever
+  the oracle's top-2 margin exceeds 1e-2), for device and for host `x`;
+* error behaviour: unbound weights, oversized batches and missing workspaces fail loudly.
+"""
+import numpy as np
+import pytest
+import torch
+
+from certifiedgpt_b200.config import LlmConfig, ModelConfig, QFormerConfig, VitConfig
+from certifiedgpt_b200.weights import random_state_dict, round_to_bf16
+from oracle import model_oracle as mo
+from oracle import smoothing_oracle as so
+
+pytestmark = pytest.mark.gpu
+REL = 2e-2
+MARGIN = 1e-2
+
+WIDE = ModelConfig(vit=VitConfig(img_size=56, depth=2), qf=QFormerConfig(layers=2),
+                   llm=LlmConfig(hidden=512, layers=2, heads=4, inter=1024, vocab=512))
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def _setup(cfg, seed, max_new=3, n_classes=8, prefix=(1, 5, 6), suffix=(7, 8, 9, 10, 11), use_graphs=True,
+           early_exit=True, oracle=False):
+    from certifiedgpt_b200.engine import MiniGPT4Engine
+    from certifiedgpt_b200.native import NativeMiniGPT4Engine
+    sd = round_to_bf16(random_state_dict(cfg, seed=seed))
+    V = cfg.llm.vocab
+    table = [((t,), t % (n_classes - 1)) for t in range(3, V)]
+    table += [((t, u), (t + u) % (n_classes - 1)) for t in range(3, V, 7) for u in range(3, V, 5)]
+    py = MiniGPT4Engine(cfg, sd, prefix, suffix, table, n_classes, max_new_tokens=max_new, use_graphs=False,
+                        early_exit=early_exit)
+    nat = NativeMiniGPT4Engine.from_engine(py, use_graphs=use_graphs)
+    orc = mo.MiniGPT4ClassifierOracle(sd, cfg, prefix, suffix, table, n_classes, max_new_tokens=max_new) if oracle else None
+    return sd, py, nat, orc
+
+
+@pytest.mark.parametrize("name,cfg", [("tiny", ModelConfig.tiny()), ("wide", WIDE)])
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_noisy_labels_bit_identical_to_python_twin(name, cfg, use_graphs):
+    sd, py, nat, _ = _setup(cfg, seed=5, use_graphs=use_graphs)
+    S = cfg.vit.img_size
+    x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(3)).cuda()
+    for first, B in [(0, 7), (7, 16), (100, 7)]:      # a repeated batch size replays the captured graph
+        got = nat.noisy_labels(x, B, 0.5, seed=11, stream_id=2, first_sample=first)
+        want = py.noisy_labels(x, B, 0.5, seed=11, stream_id=2, first_sample=first)
+        torch.cuda.synchronize()
+        assert torch.equal(got.cpu(), want.cpu()), (first, B)
+        assert nat.last_steps == py.last_steps
+
+
+def test_subsystem_entry_points_match_twin_and_oracle():
+    cfg = WIDE
+    sd, py, nat, orc = _setup(cfg, seed=21, use_graphs=False, oracle=True)
+    from certifiedgpt_b200 import _lib as L
+    g = torch.Generator().manual_seed(9)
+    B, S = 5, cfg.vit.img_size
+    images = torch.randn(B, 3, S, S, generator=g)
+    # patches of B clean images (sigma = 0), as the twin's forward_images builds them
+    patches = torch.cat([L.noise_patchify(images[b].cuda().contiguous(), 1, 0.0) for b in range(B)])
+    got = {}
+    py.forward_images(images.cuda(), collect=got)
+    tokens = nat.vit_forward(patches)
+    queries, inputs_llama = nat.qformer_forward(tokens)
+    ids, margins, steps = nat.llm_prefill_decode(queries)
+    torch.cuda.synchronize()
+    # bit-identical to the Python-driven kernel sequence
+    assert torch.equal(tokens.float().cpu(), got["image_embeds"].cpu())
+    assert torch.equal(queries.float().cpu(), got["qformer"].cpu())
+    assert torch.equal(ids.cpu(), got["ids"].cpu())
+    assert torch.equal(margins.cpu(), got["margins"].cpu())
+    assert steps == py.last_steps
+    # and within bf16 tolerance of the fp32 oracle (reference eva_vit / Qformer / HF Llama restatement)
+    ref = {}
+    with torch.no_grad():
+        img = mo.encode_img(sd, cfg, images, collect=ref)
+        embeds = mo.build_prompt_embeds(sd, cfg, img, orc.prefix_ids, orc.suffix_ids)
+        rids, first_logits, rmargins = mo.generate_ids(sd, cfg, embeds, orc.max_new_tokens)
+    assert _rel(tokens, ref["image_embeds"]) < REL
+    assert _rel(inputs_llama, img) < REL
+    safe = (rmargins > MARGIN).all(dim=1)
+    assert safe.float().mean() > 0.5
+    assert torch.equal(ids.cpu().long()[safe], rids[safe])
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_smooth_native_matches_oracle_on_injected_noise(use_graphs):
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    cfg = ModelConfig.tiny()
+    n_classes = 6
+    sd, py, nat, orc = _setup(cfg, seed=1, max_new=2, n_classes=n_classes, use_graphs=use_graphs, oracle=True)
+    S = cfg.vit.img_size
+    x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(1000))
+    n0, n, sigma, alpha = 24, 72, 0.25, 0.001
+    eps = torch.randn(n0 + n, 3, S, S, generator=torch.Generator().manual_seed(1234))
+    sm = Smooth(nat, n_classes, sigma)
+    sm.inject_noise(eps.cuda())
+    label, radius = sm.certify(x.cuda(), n0, n, alpha, 32)
+    got_sel, got_est = sm.last_counts_selection.cpu().numpy(), sm.last_counts_estimation.cpu().numpy()
+    # the Python twin on the same injected noise: identical counts, label, radius
+    sp = Smooth(py, n_classes, sigma)
+    sp.inject_noise(eps.cuda())
+    plabel, pradius = sp.certify(x.cuda(), n0, n, alpha, 32)
+    assert np.array_equal(got_sel, sp.last_counts_selection.cpu().numpy())
+    assert np.array_equal(got_est, sp.last_counts_estimation.cpu().numpy())
+    assert (label, radius) == (plabel, pradius)
+    # the oracle: counts may differ only where its top-2 margin is below 1e-2
+    cur = {"base": 0}
+    oracle = so.SmoothOracle(orc, n_classes, sigma, noise_fn=lambda d, c, b: eps[cur["base"] + d: cur["base"] + d + c])
+    sel = oracle._sample_noise(x, n0, 32)
+    cur["base"] = n0
+    est = oracle._sample_noise(x, n, 32)
+    assert got_sel.sum() == n0 and got_est.sum() == n
+    unsafe = int((np.array(oracle.last_margins) <= MARGIN).sum()) if hasattr(oracle, "last_margins") else 8
+    assert np.abs(got_sel - sel).sum() + np.abs(got_est - est).sum() <= 2 * max(unsafe, 4)
+    if np.array_equal(got_sel, sel) and np.array_equal(got_est, est):
+        ref = so.certify_tail(sel, est, n, alpha, sigma)
+        assert label == ref[0] and abs(radius - ref[1]) <= 1e-9 * max(1.0, abs(ref[1]))
+
+
+def test_certify_predict_host_x_and_batch_size_invariance():
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    cfg = ModelConfig.tiny()
+    n_classes = 6
+    sd, py, nat, _ = _setup(cfg, seed=2, max_new=2, n_classes=n_classes)
+    S = cfg.vit.img_size
+    x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(7))
+    res = []
+    for xin, bs in [(x.cuda(), 40), (x, 40), (x.pin_memory(), 17), (x.cuda(), 200)]:
+        sm = Smooth(nat, n_classes, 0.5, seed=3)       # Philox draws keyed by global sample index
+        out = sm.certify(xin, 20, 100, 0.001, bs)
+        res.append((out, sm.last_counts_selection.cpu().numpy().copy(), sm.last_counts_estimation.cpu().numpy().copy()))
+    for r in res[1:]:
+        assert r[0] == res[0][0]
+        assert np.array_equal(r[1], res[0][1]) and np.array_equal(r[2], res[0][2])
+    # Python twin, sequential (non-fused) phases: same counts
+    sp = Smooth(py, n_classes, 0.5, seed=3, fuse_selection=False)
+    assert sp.certify(x.cuda(), 20, 100, 0.001, 40) == res[0][0]
+    assert np.array_equal(sp.last_counts_estimation.cpu().numpy(), res[0][2])
+    # predict
+    sm = Smooth(nat, n_classes, 0.5, seed=3)
+    sp = Smooth(py, n_classes, 0.5, seed=3)
+    assert sm.predict(x, 64, 0.001, 25) == sp.predict(x.cuda(), 64, 0.001, 25)
+    assert np.array_equal(sm.last_counts.cpu().numpy(), sp.last_counts.cpu().numpy())
+    assert abs(sm.last_pvalue - sp.last_pvalue) <= 1e-15
+    # _sample_noise keeps the reference's return type
+    c = Smooth(nat, n_classes, 0.5, seed=3)._sample_noise(x.cuda(), 50, 16)
+    assert isinstance(c, np.ndarray) and c.dtype.kind == "i" and c.sum() == 50 and len(c) == n_classes
+
+
+def test_eos_early_exit_matches_twin():
+    cfg = ModelConfig.tiny()
+    from certifiedgpt_b200.engine import MiniGPT4Engine
+    from certifiedgpt_b200.native import NativeMiniGPT4Engine
+    sd = random_state_dict(cfg, seed=33)
+    sd["llama_model.lm_head.weight"][cfg.llm.eos_id] *= 6.0      # EOS strongly preferred
+    sd = round_to_bf16(sd)
+    table = [((t,), t % 5) for t in range(3, cfg.llm.vocab)]
+    py = MiniGPT4Engine(cfg, sd, (1, 4), (6, 7, 8), table, 6, max_new_tokens=5, use_graphs=False)
+    S = cfg.vit.img_size
+    x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(5)).cuda()
+    want = py.noisy_labels(x, 9, 0.25, seed=1)
+    for use_graphs in (False, True):
+        nat = NativeMiniGPT4Engine.from_engine(py, use_graphs=use_graphs)
+        got = nat.noisy_labels(x, 9, 0.25, seed=1)
+        assert torch.equal(got.cpu(), want.cpu())
+        assert nat.last_steps == py.last_steps and nat.last_steps < 5     # early exit happened
+
+
+def test_native_engine_fails_loudly():
+    from certifiedgpt_b200 import _lib as L
+    from certifiedgpt_b200 import native as N
+    cfg = ModelConfig.tiny()
+    sd, py, nat, _ = _setup(cfg, seed=4)
+    h = N.lib()
+    # a handle with one weight missing cannot bind a workspace; the message names the weight
+    import ctypes as C
+    c = N.config_struct(cfg, py.P, len(py.suffix_ids), 3, 1, 8, True, True)
+    hd = C.c_void_p()
+    L.check(h.cgpt_create(C.byref(c), C.byref(hd)))
+    for name, t in py.w.items():
+        if name == "vit.1.fc2.w":
+            continue
+        rows, cols = (1, t.numel()) if t.dim() == 1 else tuple(t.shape)
+        L.check(h.cgpt_bind_weight(hd, name.encode(), L.ptr(t), rows, cols, L.DT_F32 if t.dtype == torch.float32 else L.DT_BF16))
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    rc = h.cgpt_bind_workspace(hd, L.ptr(ws), ws.numel(), 1, 1, L.stream_ptr())
+    assert rc != 0 and b"vit.1.fc2.w" in h.cgpt_last_error()
+    h.cgpt_destroy(hd)
+    # too small a workspace, and a batch beyond the bound workspace
+    need = nat.workspace_bytes(4)
+    small = torch.empty(need // 2, dtype=torch.uint8, device="cuda")
+    assert h.cgpt_bind_workspace(nat._h, L.ptr(small), small.numel(), 4, 0, L.stream_ptr()) != 0
+    nat.reserve(4)
+    lab = torch.empty(8, dtype=torch.int32, device="cuda")
+    x = torch.rand(3, cfg.vit.img_size, cfg.vit.img_size).cuda()
+    spec = nat._spec(0.25, 0, 0, 0, 0, L.BLIP_MEAN, L.BLIP_STD)
+    rc = h.cgpt_noisy_labels(nat._h, L.ptr(x), C.byref(spec), 0, 8, L.ptr(lab), L.stream_ptr())
+    assert rc != 0 and b"exceeds" in h.cgpt_last_error()
+
+
+def test_gemm_profile_hook_counts_eager_launches():
+    from certifiedgpt_b200 import native as N
+    cfg = ModelConfig.tiny()
+    sd, py, nat, _ = _setup(cfg, seed=6, use_graphs=False)
+    x = torch.rand(3, cfg.vit.img_size, cfg.vit.img_size).cuda()
+    nat.noisy_labels(x, 4, 0.25)
+    N.gemm_profile_begin()
+    nat.noisy_labels(x, 4, 0.25)
+    rec = N.gemm_profile_end()
+    v, q, l = cfg.vit, cfg.qf, cfg.llm
+    n_cross = len(q.cross_layers())
+    expect = (1 + 4 * v.depth) + (1 + q.layers * 4 + n_cross * 2) + 1 + nat.last_steps * (4 * l.layers + 1)
+    assert len(rec) == expect
+    assert all(ms >= 0 and fl > 0 for ms, fl, _ in rec)
