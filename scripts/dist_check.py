@@ -1,6 +1,8 @@
 """Multi-GPU check (run under torchrun, one rank per GPU): the counts of a Smooth.certify whose
 draws are sharded over W ranks equal the single-GPU counts bit for bit (noise keyed by global
-sample index; only the int64 count vector is all-reduced over NCCL)."""
+sample index; only the int64 count vector is all-reduced over NCCL).  Default: the native engine
+(cgpt_certify shards, histograms and all-reduces inside libcgpt through its own NCCL communicator);
+--python: engine.py + torch.distributed.all_reduce."""
 import os
 import sys
 
@@ -10,6 +12,7 @@ import torch.distributed as dist
 
 from certifiedgpt_b200.config import ModelConfig
 from certifiedgpt_b200.engine import MiniGPT4Engine
+from certifiedgpt_b200.native import NativeMiniGPT4Engine
 from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
 from certifiedgpt_b200.weights import random_state_dict, round_to_bf16
 
@@ -27,7 +30,8 @@ def main():
     prefix = [1] + torch.randint(3, V, (6,), generator=g).tolist()
     suffix = torch.randint(3, V, (12,), generator=g).tolist()
     table = [((t,), t % 9) for t in range(3, V)]
-    eng = MiniGPT4Engine(cfg, sd, prefix, suffix, table, 10, max_new_tokens=1, device=dev)
+    Engine = MiniGPT4Engine if "--python" in sys.argv else NativeMiniGPT4Engine
+    eng = Engine(cfg, sd, prefix, suffix, table, 10, max_new_tokens=1, device=dev)
     S = cfg.vit.img_size
     x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(1000)).to(dev)
     n0, n = (16, 96) if full else (100, 1000)
@@ -41,7 +45,7 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"world={world} sharded={res} single={res1} counts_est={est.tolist()} "
+        print(f"engine={Engine.__name__} world={world} sharded={res} single={res1} counts_est={est.tolist()} "
               f"{'DIST_OK' if flag.item() == 1 else 'DIST_MISMATCH'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
