@@ -395,6 +395,8 @@ int attention(const cgpt_attn_args* a, cudaStream_t stream) {
   // tcgen05 one-shot kernel for the ViT / Llama-prefill shapes; mma.sync flash kernel otherwise
   // (CGPT_ATTN_LEGACY=1 forces the flash kernel, used by the parity tests to cover both)
   static const bool legacy = getenv("CGPT_ATTN_LEGACY") != nullptr;
+  // persistent pipelined kernel for short sequences with 128-wide heads (the Llama prefill shape)
+  if (!legacy && a->decode_kernel != 2 && attn_prefill_supported(a)) return attention_prefill(a, stream);
   if (!legacy && a->decode_kernel != 2 && attn_umma_supported(a)) return attention_umma(a, stream);
   AttnParams p;
   p.q = (const __nv_bfloat16*)a->q; p.ldq = a->ldq; p.q_rows_per_batch = a->q_rows_per_batch;

@@ -70,3 +70,38 @@ def test_umma_and_flash_agree(lib):
     a = _run(lib, 3, 16, 257, 257, 88, False, False, seed=5, fused_qkv=True)
     b = _run(lib, 3, 16, 257, 257, 88, False, True, seed=5, fused_qkv=True)
     assert (a.float() - b.float()).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,rows,causal", [
+    (40, 32, 72, 79, 83, True),      # the smoothing path's prefill: 1280 items -> ~9 per persistent CTA
+    (300, 4, 72, 79, 83, True),
+    (37, 8, 128, 128, 128, True),    # largest shape: a single load stage (no S-ahead issue)
+    (50, 8, 5, 16, 20, True),        # tiny tiles: the 128-row UMMA operand reads past the sub-tiles
+    (33, 8, 64, 48, 48, False),
+    (1, 32, 7, 7, 7, True),          # the shared-prefix pass
+])
+def test_persistent_prefill_kernel_kv_cache_layout(lib, B, H, Tq, Tk, rows, causal):
+    """attn_prefill.cu: many (sample, head) items per CTA through the load ring / two TMEM stages, keys read
+    out of a KV cache whose rows beyond Tk hold finite garbage (must be masked, not multiplied in)."""
+    hd, D = 128, H * 128
+    g = torch.Generator(device="cuda").manual_seed(B + Tq)
+    q = torch.randn(B * Tq, D, device="cuda", generator=g).bfloat16()
+    kc = torch.full((B, rows, D), 50.0, device="cuda").bfloat16()
+    vc = torch.full((B, rows, D), -70.0, device="cuda").bfloat16()
+    kc[:, :Tk] = torch.randn(B, Tk, D, device="cuda", generator=g).bfloat16()
+    vc[:, :Tk] = torch.randn(B, Tk, D, device="cuda", generator=g).bfloat16()
+    out = torch.full((B * Tq, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    scale = hd ** -0.5
+    lib.attention(q, kc.view(-1, D), vc.view(-1, D), out, B=B, H=H, Tq=Tq, Tk=Tk, head_dim=hd, scale=scale,
+                  causal=causal, kv_rows_per_batch=rows)
+    torch.cuda.synchronize()
+    ref = _ref(q, kc[:, :Tk].reshape(-1, D), vc[:, :Tk].reshape(-1, D), B, H, Tq, Tk, hd, scale, causal)
+    assert not torch.isnan(out.float()).any(), "unwritten / NaN outputs"
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"max err {err}"
+    # same inputs through the mma.sync flash kernel: independent implementation, same answer
+    out2 = torch.empty_like(out)
+    lib.attention(q, kc.view(-1, D), vc.view(-1, D), out2, B=B, H=H, Tq=Tq, Tk=Tk, head_dim=hd, scale=scale,
+                  causal=causal, kv_rows_per_batch=rows, force_flash=True)
+    torch.cuda.synchronize()
+    assert (out.float() - out2.float()).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
