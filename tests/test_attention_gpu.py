@@ -105,3 +105,17 @@ def test_persistent_prefill_kernel_kv_cache_layout(lib, B, H, Tq, Tk, rows, caus
                   causal=causal, kv_rows_per_batch=rows, force_flash=True)
     torch.cuda.synchronize()
     assert (out.float() - out2.float()).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,hd,causal,fused", [
+    (40, 16, 257, 257, 88, False, True),     # ViT: 640 items -> 4-5 per persistent CTA, cls row on CUDA cores
+    (100, 4, 130, 200, 96, False, False),
+    (70, 4, 64, 48, 104, False, False),      # one q-tile, Q pad columns stay zero across items
+    (80, 8, 200, 256, 128, True, False),
+])
+def test_persistent_one_shot_kernel_many_items(lib, B, H, Tq, Tk, hd, causal, fused):
+    """attn_umma.cu walks several (sample, head) items per CTA: barrier parities, x-buffer double buffering,
+    Q pad re-zeroing and the load of item i+1 issued under the epilogue of item i."""
+    a = _run(lib, B, H, Tq, Tk, hd, causal, False, seed=3, fused_qkv=fused)
+    b = _run(lib, B, H, Tq, Tk, hd, causal, True, seed=3, fused_qkv=fused)
+    assert (a.float() - b.float()).abs().max().item() < 2e-2
