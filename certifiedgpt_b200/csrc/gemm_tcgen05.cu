@@ -67,6 +67,7 @@ struct EpiParams {
   int remap_stride;   // out row = (m / period) * remap_stride + remap_offset + (m % period)
   int remap_offset;
   int red_inplace;    // out aliases the fp32 residual: accumulate with red.global.add (no residual load)
+  int group_m;        // m-tiles per rasterisation band (tile_coords)
   long long* dbg;     // optional per-CTA cycle counters (CGPT_GEMM_DBG): [grid][8]
 };
 
@@ -220,16 +221,16 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams&
   }
 }
 
-// Tile rasterisation: bands of GROUP_M m-tiles, m fastest inside a band.  The CTAs running at any
-// moment then share ~GROUP_M A tiles and only ~(#CTAs / GROUP_M) weight tiles, so the working set
+// Tile rasterisation: bands of group_m m-tiles, m fastest inside a band.  The CTAs running at any
+// moment then share ~group_m A tiles and only ~(#CTAs / group_m) weight tiles, so the working set
 // stays inside the 126 MB L2 even for the 180 MB Llama gate/up weight (n-fastest order re-read the
 // whole weight from HBM once per m-tile: 35 GB of DRAM reads for 0.77 GB of operands, ncu r01).
-constexpr int GROUP_M = 16;
-__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& m, int& n) {
-  const int band = GROUP_M * n_tiles;
+constexpr int GROUP_M_MAX = 16;
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int group_m, int& m, int& n) {
+  const int band = group_m * n_tiles;
   const int g = tile / band;
-  const int first_m = g * GROUP_M;
-  const int gm = min(GROUP_M, m_tiles - first_m);
+  const int first_m = g * group_m;
+  const int gm = min(group_m, m_tiles - first_m);
   const int r = tile - g * band;
   m = first_m + r % gm;
   n = r / gm;
@@ -298,7 +299,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         int m_blk, n_blk;
-        tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
+        tile_coords(tile, m_tiles, n_tiles, epi.group_m, m_blk, n_blk);
         m_blk = m_blk * CTAS + cta_rank;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -380,7 +381,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     long long t_wait_mma = 0, t_work = 0, t_bar = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int m_blk, n_blk;
-      tile_coords(tile, m_tiles, n_tiles, m_blk, n_blk);
+      tile_coords(tile, m_tiles, n_tiles, epi.group_m, m_blk, n_blk);
       m_blk = m_blk * CTAS + cta_rank;
       const int n_base = n_blk * BN;
       float* bias_s = bias_smem + acc * 256;
@@ -564,6 +565,14 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   // masked tail; 1-CTA tiles prefer an exact divisor of N
   int bn = (force_bn & 0xfff);
   if (bn == 0) bn = ctas == 2 ? (N > 176 ? 256 : (N > 128 ? 176 : 128)) : pick_bn(N);
+  {
+    // 16 m-tiles per band.  Measured (ncu, profiles/r01_gemm_band_traffic.txt): shrinking the band for the
+    // long-K residual GEMMs (6 tiles at K = 11008 so that the A band is 34 MB instead of 90 MB) does not lower
+    // their DRAM reads (14.9 vs 13.6 GB for Llama down) and costs nothing in time either way, so the band stays
+    // fixed; CGPT_GEMM_GROUP_M overrides it for experiments.
+    static const int forced = getenv("CGPT_GEMM_GROUP_M") ? atoi(getenv("CGPT_GEMM_GROUP_M")) : 0;
+    p.group_m = forced > 0 ? forced : GROUP_M_MAX;
+  }
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, A, M, K, lda, BM)) return rc;
   if (int rc = make_tmap(&tb, W, N, K, ldw, bn / ctas)) return rc;
