@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcgpt.so")
 
 DT_BF16, DT_F32 = 0, 1
-ACT_NONE, ACT_GELU, ACT_SWIGLU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_SWIGLU, ACT_QUICKGELU = 0, 1, 2, 3
 NOISE_GAUSSIAN, NOISE_UNIFORM = 0, 1
 SPACE_NORMALIZED, SPACE_PIXEL = 0, 1
 
@@ -101,6 +101,7 @@ def _EXTRA_SIGS(vp, i64, i32, f32, f64, u64):
         "cgpt_attention": [C.POINTER(AttnArgs), vp],
         "cgpt_rope_split": [vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, i32, i32, vp],
         "cgpt_gather_rows": [vp, i64, vp, i32, i32, i32, vp, i64, i32, i32, i32, i32, vp],
+        "cgpt_cosine_rows": [vp, i64, i32, i32, vp, vp, vp],
         "cgpt_gemm_profile_begin": [],
         "cgpt_gemm_profile_end": [vp, vp, i32, C.POINTER(C.c_int)],
     }
@@ -385,3 +386,15 @@ def greedy_step(next_idx, finished, ids_out, t, eos_id, pad_id, unfinished_count
     lib = load()
     check(lib.cgpt_greedy_step(ptr(next_idx), next_idx.numel(), ptr(finished), ptr(ids_out),
                                ids_out.stride(0), t, eos_id, pad_id, ptr(unfinished_count), stream_ptr()))
+
+
+def cosine_rows(feats, target, out=None):
+    """scores[r] = cos(feats[r], target), fp32 (CLIP feature scoring of the attack loop)."""
+    lib = load()
+    assert feats.dtype == torch.float32 and target.dtype == torch.float32 and feats.stride(1) == 1
+    rows, D = feats.shape
+    assert target.numel() == D and target.is_contiguous()
+    if out is None:
+        out = torch.empty(rows, dtype=torch.float32, device=feats.device)
+    check(lib.cgpt_cosine_rows(ptr(feats), feats.stride(0), rows, D, ptr(target), ptr(out), stream_ptr()))
+    return out

@@ -90,6 +90,11 @@ int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int3
                       (cudaStream_t)stream);
 }
 
+int cgpt_cosine_rows(const float* feats, int64_t ld, int rows, int D, const float* target, float* scores,
+                     void* stream) {
+  return cosine_rows(feats, ld, rows, D, target, scores, (cudaStream_t)stream);
+}
+
 int cgpt_norm_rows(const void* x, int64_t ldx, int in_dtype, const float* gamma, const float* beta,
                    float eps, int rows, int D, void* out, int64_t ldo, int out_dtype, int rms,
                    int in_row_period, int in_row_stride, int in_row_offset, void* stream) {

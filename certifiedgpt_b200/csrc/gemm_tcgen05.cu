@@ -138,6 +138,11 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
 #pragma unroll
     for (int i = 0; i < NC; ++i) v[i] = gelu_erf_fast(v[i]);
   }
+  if (p.act == CGPT_ACT_QUICKGELU) {
+    // x * sigmoid(1.702 x) (CLIP's quick_gelu)
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = v[i] * rcp_approx(1.0f + ex2_approx(-1.702f * 1.4426950408889634f * v[i]));
+  }
   if (p.act == CGPT_ACT_SWIGLU) {
     // weight rows are interleaved (gate_j, up_j): out[:, j] = silu(gate_j) * up_j
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + (n0 >> 1);

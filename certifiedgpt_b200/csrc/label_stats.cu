@@ -380,4 +380,32 @@ uint64_t answer_hash_host(const int* ids, int n, int eos_id) {
   return h;
 }
 
+
+// ------------------------------------------------------------------ cosine of feature rows against one target
+__global__ void __launch_bounds__(128) cosine_rows_kernel(const float* __restrict__ feats, long long ld, int rows, int D,
+                                                          const float* __restrict__ target, float* __restrict__ scores) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* f = feats + r * ld;
+  float dot = 0.f, nf = 0.f, nt = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float a = f[c], b = __ldg(target + c);
+    dot = fmaf(a, b, dot);
+    nf = fmaf(a, a, nf);
+    nt = fmaf(b, b, nt);
+  }
+  dot = warp_sum(dot); nf = warp_sum(nf); nt = warp_sum(nt);
+  if (lane == 0) scores[r] = dot / fmaxf(sqrtf(nf) * sqrtf(nt), 1e-12f);
+}
+
+int cosine_rows(const float* feats, long long ld, int rows, int D, const float* target, float* scores,
+                cudaStream_t stream) {
+  CGPT_REQUIRE(feats && target && scores && rows > 0 && D > 0, "cosine_rows: bad arguments rows=%d D=%d", rows, D);
+  cosine_rows_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(feats, ld, rows, D, target, scores);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace cgpt

@@ -36,6 +36,8 @@ int certify_tail(const long long* counts_sel, const long long* counts_est, int n
                  double alpha, double sigma, int* out_label, double* out_stats, cudaStream_t stream);
 int predict_tail(const long long* counts, int num_classes, double alpha, int* out_label,
                  double* out_stats, cudaStream_t stream);
+int cosine_rows(const float* feats, long long ld, int rows, int D, const float* target, float* scores,
+                cudaStream_t stream);
 int norm_rows(const void* x, long long ldx, int in_dtype, const float* gamma, const float* beta,
               float eps, int rows, int D, void* out, long long ldo, int out_dtype, int rms,
               int in_row_period, int in_row_stride, int in_row_offset, cudaStream_t stream);

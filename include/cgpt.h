@@ -28,7 +28,7 @@ extern "C" {
 #define CGPT_ABI_VERSION 2
 
 enum { CGPT_DT_BF16 = 0, CGPT_DT_F32 = 1 };
-enum { CGPT_ACT_NONE = 0, CGPT_ACT_GELU = 1, CGPT_ACT_SWIGLU = 2 };
+enum { CGPT_ACT_NONE = 0, CGPT_ACT_GELU = 1, CGPT_ACT_SWIGLU = 2, CGPT_ACT_QUICKGELU = 3 /* x*sigmoid(1.702x), CLIP */ };
 enum { CGPT_NOISE_GAUSSIAN = 0, CGPT_NOISE_UNIFORM = 1 };
 /* where the noise is added relative to the BLIP Normalize step
  * (processors/base_processor.py:17-34):
@@ -122,6 +122,11 @@ int cgpt_certify_tail(const int64_t* counts_sel, const int64_t* counts_est, int 
  * out_stats[0] = p-value, [1],[2] = top-2 counts */
 int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int32_t* out_label,
                       double* out_stats, void* stream);
+
+/* scores[r] = cos(feats[r, :], target) in fp32 (one warp per row): the CLIP feature cosine of the black-box
+ * attack loop (BASELINE.json configs[4]; README.md:62-64 - the reference ships no code for it) */
+int cgpt_cosine_rows(const float* feats, int64_t ld, int rows, int D, const float* target, float* scores,
+                     void* stream);
 
 /* ---------------------------------------------------------------- norms
  * LayerNorm (rms = 0) or RMSNorm (rms = 1) over rows of width D; fp32 statistics.
