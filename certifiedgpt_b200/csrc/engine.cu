@@ -9,6 +9,7 @@
 // workspace the caller allocates (cgpt_workspace_bytes).
 #include <dlfcn.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -44,6 +45,21 @@ __global__ void set_rows_f32_kernel(float* __restrict__ out, long long row_strid
                                     int D) {
   float* o = out + blockIdx.x * row_stride;
   for (int c = threadIdx.x; c < D; c += blockDim.x) o[c] = vec[c];
+}
+
+// dst[b, :] = src[b * T + T - 1, :]  (rows of `row_bytes` bytes, multiple of 16): the last prompt position of
+// every sample, the only row the last decoder layer still needs after its attention
+__global__ void gather_last_rows_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, int T, int vec_per_row) {
+  const uint4* s = src + (static_cast<long long>(blockIdx.x) * T + T - 1) * vec_per_row;
+  uint4* d = dst + static_cast<long long>(blockIdx.x) * vec_per_row;
+  for (int c = threadIdx.x; c < vec_per_row; c += blockDim.x) d[c] = s[c];
+}
+int gather_last_rows(void* dst, const void* src, int T, int B, long long row_bytes, cudaStream_t s) {
+  gather_last_rows_kernel<<<B, 256, 0, s>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), T,
+                                            static_cast<int>(row_bytes / 16));
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
 }
 
 int fill_u32(void* p, long long n, uint32_t v, cudaStream_t s) {
@@ -93,7 +109,7 @@ struct Buffers {   // all inside the caller's workspace
   void *patches, *v_res, *v_xn, *v_qkv, *v_att, *v_h, *v_out;
   void *q_h, *q_tmp, *q_qkv, *q_ctx, *q_cq, *q_ckv, *q_inter, *enc_out;
   // language side
-  void *l_res, *l_xn, *l_qkv, *l_att, *l_act, *kc, *vc, *kp, *vp, *l_last, *l_logits;
+  void *l_res, *l_xn, *l_qkv, *l_att, *l_act, *kc, *vc, *kp, *vp, *l_last, *l_logits, *l_res_last, *l_att_last;
   int32_t *ids, *finished, *unfinished, *next, *cur, *labels;
   float *mcol, *margin;
   // per-call
@@ -351,6 +367,8 @@ long long layout(Engine* E, int B, bool encoder_only, char* base, Buffers* out) 
     b.kp = take(pre);
     b.vp = take(pre);
     b.l_last = take(static_cast<long long>(B) * Hl * 2);
+    b.l_res_last = take(static_cast<long long>(B) * Hl * 4);
+    b.l_att_last = take(static_cast<long long>(B) * Hl * 2);
     b.l_logits = take(static_cast<long long>(B) * c.llm_vocab * 4);
     b.ids = static_cast<int32_t*>(take(static_cast<long long>(B) * c.max_new_tokens * 4));
     b.finished = static_cast<int32_t*>(take(B * 4LL));
@@ -447,9 +465,13 @@ int qformer_forward(Engine* E, const void* image_embeds, int B, void* out_h, cud
 
 // ---------------------------------------------------------------- Llama
 // HF LlamaDecoderLayer x L on `rows` = B*T rows; K/V appended to the cache at row cache_row0 of each sample
+// last_res (nullable): the caller only needs the LAST position of every sample after the stack (prefill: the
+// position that predicts the first new token).  The last layer then still projects K/V for all rows, but its
+// o_proj, MLP and residual run on B rows instead of B*T (same per-row arithmetic);
+// the compact residual [B, hidden] fp32 lands in last_res.
 int llm_layers(Engine* E, int rows, int T, int B, void* res, void* xn, void* qkv, void* att, void* act, void* kc,
                void* vc, long long layer_stride, int pos0, int cache_row0, int cache_rows, int decode,
-               cudaStream_t s) {
+               cudaStream_t s, void* last_res = nullptr, void* last_att = nullptr) {
   const cgpt_model_config& c = E->c;
   const int Hd = c.llm_hidden;
   const float scale = 1.0f / sqrtf(static_cast<float>(E->lhd));
@@ -463,6 +485,16 @@ int llm_layers(Engine* E, int rows, int T, int B, void* res, void* xn, void* qkv
                         cache_rows, cache_row0, s));
     CGPT_TRY(attn(qkv, 3 * Hd, T, kci, vci, Hd, cache_rows, att, Hd, B, c.llm_heads, T, cache_row0 + T, E->lhd, scale,
                   1, decode, s));
+    if (last_res != nullptr && i == c.llm_layers - 1 && T > 1) {
+      CGPT_TRY(gather_last_rows(last_res, res, T, B, static_cast<long long>(Hd) * 4, s));
+      CGPT_TRY(gather_last_rows(last_att, att, T, B, static_cast<long long>(Hd) * 2, s));
+      CGPT_TRY(gemm(last_att, Hd, L.ow, B, Hd, Hd, Epi(last_res, Hd, CGPT_DT_F32).resid(last_res, Hd, CGPT_DT_F32), s));
+      CGPT_TRY(norm_rows(last_res, Hd, CGPT_DT_F32, L.n2, nullptr, c.llm_rms_eps, B, Hd, xn, Hd, CGPT_DT_BF16, 1, 0, 0, 0, s));
+      CGPT_TRY(gemm(xn, Hd, L.guw, B, 2 * c.llm_inter, Hd, Epi(act, c.llm_inter, CGPT_DT_BF16).act(CGPT_ACT_SWIGLU), s));
+      CGPT_TRY(gemm(act, c.llm_inter, L.downw, B, Hd, c.llm_inter,
+                    Epi(last_res, Hd, CGPT_DT_F32).resid(last_res, Hd, CGPT_DT_F32), s));
+      return 0;
+    }
     CGPT_TRY(gemm(att, Hd, L.ow, rows, Hd, Hd, Epi(res, Hd, CGPT_DT_F32).resid(res, Hd, CGPT_DT_F32), s));
     CGPT_TRY(norm_rows(res, Hd, CGPT_DT_F32, L.n2, nullptr, c.llm_rms_eps, rows, Hd, xn, Hd, CGPT_DT_BF16, 1, 0, 0, 0, s));
     CGPT_TRY(gemm(xn, Hd, L.guw, rows, 2 * c.llm_inter, Hd, Epi(act, c.llm_inter, CGPT_DT_BF16).act(CGPT_ACT_SWIGLU), s));
@@ -521,13 +553,20 @@ int llm_prefill_first(Engine* E, const void* qf_out, int B, cudaStream_t s) {
                 Epi(b.l_res, Hd, CGPT_DT_F32).bias(E->proj_b).remap(nq, Tp, 0), s));
   if (ns > 0)
     CGPT_TRY(gather_rows(E->emb, Hd, E->suffix_ids, ns, B * ns, Hd, b.l_res, Hd, CGPT_DT_F32, ns, Tp, nq, s));
+  // the last layer only needs the last prompt position of every sample (CGPT_NO_LAST_PRUNE=1: A/B switch)
+  static const bool no_prune = getenv("CGPT_NO_LAST_PRUNE") != nullptr;
+  const bool prune = Tp > 1 && !no_prune;
   CGPT_TRY(llm_layers(E, M, Tp, B, b.l_res, b.l_xn, b.l_qkv, b.l_att, b.l_act, b.kc, b.vc, layer_stride, P, P,
-                      E->cache_rows, 0, s));
+                      E->cache_rows, 0, s, prune ? b.l_res_last : nullptr, b.l_att_last));
   CGPT_TRY(fill_u32(b.ids, static_cast<long long>(B) * mn, static_cast<uint32_t>(c.pad_id), s));
   CGPT_CHECK_CUDA(cudaMemsetAsync(b.finished, 0, B * 4LL, s));
   CGPT_TRY(fill_u32(b.margin, static_cast<long long>(B) * mn, 0x7f800000u /* +inf */, s));
-  CGPT_TRY(norm_rows(b.l_res, Hd, CGPT_DT_F32, E->llm_norm, nullptr, c.llm_rms_eps, B, Hd, b.l_last, Hd, CGPT_DT_BF16, 1,
-                     1, Tp, Tp - 1, s));
+  if (prune)
+    CGPT_TRY(norm_rows(b.l_res_last, Hd, CGPT_DT_F32, E->llm_norm, nullptr, c.llm_rms_eps, B, Hd, b.l_last, Hd,
+                       CGPT_DT_BF16, 1, 0, 0, 0, s));
+  else
+    CGPT_TRY(norm_rows(b.l_res, Hd, CGPT_DT_F32, E->llm_norm, nullptr, c.llm_rms_eps, B, Hd, b.l_last, Hd, CGPT_DT_BF16, 1,
+                       1, Tp, Tp - 1, s));
   return head_and_pick(E, B, 0, s);
 }
 

@@ -265,7 +265,10 @@ class MiniGPT4Engine:
 
     # ------------------------------------------------------------------ Llama
     def _llm_layers(self, rows, T, B, res, xn, qkv, att, act, kc, vc, pos0, cache_row0, cache_rows,
-                    decode=False):
+                    decode=False, last_only=False):
+        """last_only: the caller needs only the LAST position of every sample after the stack (prefill): the last
+        layer still projects K/V for all rows, but its o_proj / MLP / residual run on B rows instead of B*T (same
+        per-row arithmetic); returns the compact residual [B, hidden] fp32."""
         l, w = self.cfg.llm, self.w
         Hd = l.hidden
         scale = 1.0 / math.sqrt(l.head_dim)
@@ -278,10 +281,19 @@ class MiniGPT4Engine:
             Tk = cache_row0 + T
             L.attention(qkv[:, :Hd], kc[i].view(-1, Hd), vc[i].view(-1, Hd), att, B=B, H=l.heads, Tq=T, Tk=Tk,
                         head_dim=l.head_dim, scale=scale, kv_rows_per_batch=cache_rows, causal=True, decode=decode)
+            if last_only and i == l.layers - 1 and T > 1:
+                res_last = res.view(B, T, Hd)[:, T - 1].contiguous()
+                att_last = att.view(B, T, Hd)[:, T - 1].contiguous()
+                L.gemm(att_last, w[o + "o.w"], resid=res_last, out=res_last)
+                L.norm_rows(res_last, w[o + "n2"], None, l.rms_eps, xn[:B], rms=True)
+                L.gemm(xn[:B], w[o + "gu.w"], act=L.ACT_SWIGLU, out=act[:B])
+                L.gemm(act[:B], w[o + "down.w"], resid=res_last, out=res_last)
+                return res_last
             L.gemm(att, w[o + "o.w"], resid=res, out=res)
             L.norm_rows(res, w[o + "n2"], None, l.rms_eps, xn, rms=True)
             L.gemm(xn, w[o + "gu.w"], act=L.ACT_SWIGLU, out=act)
             L.gemm(act, w[o + "down.w"], resid=res, out=res)
+        return None
 
     def _build_prefix_cache(self):
         """K/V of the batch-invariant prompt prefix ("<s>[INST] <Img>", the tokens BEFORE the image),
@@ -318,14 +330,17 @@ class MiniGPT4Engine:
         if collect is not None:
             collect["llm_in"] = res.view(B, Tp, Hd).clone()
         # A12 prefill: per-sample rows attend to the shared prefix K/V + their own causal rows
-        self._llm_layers(M, Tp, B, res, xn, qkv, att, act, kc, vc, pos0=P, cache_row0=P,
-                         cache_rows=self.cache_rows)
+        res_last = self._llm_layers(M, Tp, B, res, xn, qkv, att, act, kc, vc, pos0=P, cache_row0=P,
+                                    cache_rows=self.cache_rows, last_only=True)
         last = buf["l.last"][:B]
         ids, fin, margin = buf["ids"][:B], buf["finished"][:B], buf["margin"][:B]
         ids.fill_(l.pad_id)
         fin.zero_()
         margin.fill_(float("inf"))
-        L.norm_rows(res, w["llm.norm"], None, l.rms_eps, last, rms=True, gather=(1, Tp, Tp - 1))
+        if res_last is not None:
+            L.norm_rows(res_last, w["llm.norm"], None, l.rms_eps, last, rms=True)
+        else:
+            L.norm_rows(res, w["llm.norm"], None, l.rms_eps, last, rms=True, gather=(1, Tp, Tp - 1))
         self._head_and_pick(B, buf, 0, collect)
 
     def _head_and_pick(self, B, buf, t, collect=None):
