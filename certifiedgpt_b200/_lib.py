@@ -20,6 +20,14 @@ class CgptError(RuntimeError):
     pass
 
 
+class GemmRope(C.Structure):
+    _fields_ = [
+        ("T", C.c_int), ("heads", C.c_int), ("pos0", C.c_int),
+        ("cos_table", C.c_void_p), ("sin_table", C.c_void_p), ("kcache", C.c_void_p), ("vcache", C.c_void_p),
+        ("ld_cache", C.c_int64), ("cache_rows_per_batch", C.c_int), ("cache_row0", C.c_int),
+    ]
+
+
 class GemmEpilogue(C.Structure):
     _fields_ = [
         ("out", C.c_void_p), ("ldo", C.c_int64), ("out_dtype", C.c_int),
@@ -30,6 +38,7 @@ class GemmEpilogue(C.Structure):
         ("row_period", C.c_int), ("row_add_offset", C.c_int),
         ("remap_stride", C.c_int), ("remap_offset", C.c_int),
         ("max_ctas", C.c_int),
+        ("rope", C.POINTER(GemmRope)),
     ]
 
 
@@ -151,7 +160,7 @@ def gemm_profile_stop():
 
 def gemm(a, w, *, out=None, bias=None, resid=None, act=ACT_NONE, out_dtype=torch.bfloat16,
          row_add=None, row_period=0, row_add_offset=0, remap_stride=0, remap_offset=0,
-         out_rows=None, force_bn=0, max_ctas=0):
+         out_rows=None, force_bn=0, max_ctas=0, rope=None):
     """out = epilogue(a @ w.T); a [M,K] bf16 (row stride may exceed K), w [N,K] bf16."""
     lib = load()
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -179,6 +188,15 @@ def gemm(a, w, *, out=None, bias=None, resid=None, act=ACT_NONE, out_dtype=torch
     e.row_period = row_period; e.row_add_offset = row_add_offset
     e.remap_stride = remap_stride; e.remap_offset = remap_offset
     e.max_ctas = max_ctas
+    if rope is not None:
+        # fused rotary + KV-cache append (128-wide heads): dict(T, heads, pos0, cos, sin, kcache, vcache, cache_rows, cache_row0)
+        r = GemmRope()
+        r.T, r.heads, r.pos0 = rope["T"], rope["heads"], rope["pos0"]
+        r.cos_table, r.sin_table = rope["cos"].data_ptr(), rope["sin"].data_ptr()
+        r.kcache, r.vcache = rope["kcache"].data_ptr(), rope["vcache"].data_ptr()
+        r.ld_cache = rope["kcache"].stride(-2)
+        r.cache_rows_per_batch, r.cache_row0 = rope["cache_rows"], rope["cache_row0"]
+        e.rope = C.pointer(r)
     check(lib.cgpt_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K,
                              C.byref(e), force_bn, stream_ptr()))
     return out

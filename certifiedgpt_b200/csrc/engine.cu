@@ -192,6 +192,7 @@ struct Epi {
   Epi& resid(const void* r, long long ldr, int dt) { e.resid = r; e.ldr = ldr; e.resid_dtype = dt; return *this; }
   Epi& act(int a) { e.act = a; return *this; }
   Epi& row_add(const float* p, long long ld, int offset) { e.row_add = p; e.ld_row_add = ld; e.row_add_offset = offset; return *this; }
+  Epi& rope(const cgpt_gemm_rope* r) { e.rope = r; return *this; }
   Epi& remap(int period, int stride, int offset) { e.row_period = period; e.remap_stride = stride; e.remap_offset = offset; return *this; }
 };
 inline int gemm(const void* A, long long lda, const void* W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
@@ -475,14 +476,26 @@ int llm_layers(Engine* E, int rows, int T, int B, void* res, void* xn, void* qkv
   const cgpt_model_config& c = E->c;
   const int Hd = c.llm_hidden;
   const float scale = 1.0f / sqrtf(static_cast<float>(E->lhd));
+  static const bool no_fused_rope = getenv("CGPT_NO_FUSED_ROPE") != nullptr;   // A/B switch
+  const bool fused_rope = E->lhd == 128 && !no_fused_rope;
   for (int i = 0; i < c.llm_layers; ++i) {
     const LlmLayer& L = E->llm[i];
     void* kci = bf(kc) + i * layer_stride;
     void* vci = bf(vc) + i * layer_stride;
     CGPT_TRY(norm_rows(res, Hd, CGPT_DT_F32, L.n1, nullptr, c.llm_rms_eps, rows, Hd, xn, Hd, CGPT_DT_BF16, 1, 0, 0, 0, s));
-    CGPT_TRY(gemm(xn, Hd, L.qkvw, rows, 3 * Hd, Hd, Epi(qkv, 3 * Hd, CGPT_DT_BF16), s));
-    CGPT_TRY(rope_split(qkv, 3 * Hd, rows, T, c.llm_heads, E->lhd, pos0, E->rope_cos, E->rope_sin, kci, vci, Hd,
-                        cache_rows, cache_row0, s));
+    if (fused_rope) {
+      // rotary embedding + KV-cache append inside the QKV GEMM's epilogue (128-wide heads)
+      cgpt_gemm_rope r;
+      r.T = T; r.heads = c.llm_heads; r.pos0 = pos0;
+      r.cos_table = E->rope_cos; r.sin_table = E->rope_sin;
+      r.kcache = kci; r.vcache = vci; r.ld_cache = Hd;
+      r.cache_rows_per_batch = cache_rows; r.cache_row0 = cache_row0;
+      CGPT_TRY(gemm(xn, Hd, L.qkvw, rows, 3 * Hd, Hd, Epi(qkv, 3 * Hd, CGPT_DT_BF16).rope(&r), s));
+    } else {
+      CGPT_TRY(gemm(xn, Hd, L.qkvw, rows, 3 * Hd, Hd, Epi(qkv, 3 * Hd, CGPT_DT_BF16), s));
+      CGPT_TRY(rope_split(qkv, 3 * Hd, rows, T, c.llm_heads, E->lhd, pos0, E->rope_cos, E->rope_sin, kci, vci, Hd,
+                          cache_rows, cache_row0, s));
+    }
     CGPT_TRY(attn(qkv, 3 * Hd, T, kci, vci, Hd, cache_rows, att, Hd, B, c.llm_heads, T, cache_row0 + T, E->lhd, scale,
                   1, decode, s));
     if (last_res != nullptr && i == c.llm_layers - 1 && T > 1) {

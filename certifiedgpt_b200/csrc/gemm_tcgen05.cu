@@ -68,6 +68,11 @@ struct EpiParams {
   int remap_offset;
   int red_inplace;    // out aliases the fp32 residual: accumulate with red.global.add (no residual load)
   int group_m;        // m-tiles per rasterisation band (tile_coords)
+  // fused HF rotary embedding + KV-cache append for a fused QKV projection with 128-wide heads (ROPE kernels)
+  int rope_T, rope_pos0, rope_hidden;          // rows per sample, position of row 0, heads * 128
+  const float* rope_cos; const float* rope_sin; // [max_pos, 64]
+  __nv_bfloat16* rope_k; __nv_bfloat16* rope_v; // KV cache
+  long long rope_ldc; int rope_cache_rows, rope_cache_row0;
   long long* dbg;     // optional per-CTA cycle counters (CGPT_GEMM_DBG): [grid][8]
 };
 
@@ -226,6 +231,65 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams&
   }
 }
 
+// Fused QKV epilogue (ROPE kernels): this warp's 128 accumulator columns are exactly one head of q, k or v.
+// q and k get HF's rotary embedding (rotate_half convention: out[j] = x[j] cos_j - x[j+64] sin_j,
+// out[j+64] = x[j+64] cos_j + x[j] sin_j) on the fp32 accumulators; q goes to the q part of `out`, rotated k and
+// plain v go straight to the KV cache row of (sample, position): the separate rope / cache-append pass and its
+// round trip through the QKV buffer disappear.
+__device__ __forceinline__ void epilogue_rope_head(uint32_t t_row, const EpiParams& p, int m, bool row_ok, int col0) {
+  const int region = col0 / p.rope_hidden;            // 0 = q, 1 = k, 2 = v
+  const int cin = col0 - region * p.rope_hidden;      // column inside q / k / v
+  const int b = m / p.rope_T, i = m - b * p.rope_T;
+  const int pos = p.rope_pos0 + i;
+  __nv_bfloat16* dst;
+  if (region == 0) {
+    dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldo + cin;
+  } else {
+    const long long crow = (static_cast<long long>(b) * p.rope_cache_rows + p.rope_cache_row0 + i) * p.rope_ldc;
+    dst = (region == 1 ? p.rope_k : p.rope_v) + crow + cin;
+  }
+  const float* cs = p.rope_cos + static_cast<long long>(pos) * 64;
+  const float* sn = p.rope_sin + static_cast<long long>(pos) * 64;
+  uint32_t lo[16], hi[16];
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld_x16(t_row + c * 16, lo);
+    tmem_ld_x16(t_row + 64 + c * 16, hi);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    uint32_t w1[8], w2[8];
+    if (region < 2) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + c * 16 + j));
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn + c * 16 + j));
+        const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+        float o1[4], o2[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float x1 = __uint_as_float(lo[j + t]), x2 = __uint_as_float(hi[j + t]);
+          o1[t] = x1 * cc[t] - x2 * ss[t];
+          o2[t] = x2 * cc[t] + x1 * ss[t];
+        }
+        w1[j / 2] = pack_bf16x2(o1[0], o1[1]); w1[j / 2 + 1] = pack_bf16x2(o1[2], o1[3]);
+        w2[j / 2] = pack_bf16x2(o2[0], o2[1]); w2[j / 2 + 1] = pack_bf16x2(o2[2], o2[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        w1[j / 2] = pack_bf16x2(__uint_as_float(lo[j]), __uint_as_float(lo[j + 1]));
+        w2[j / 2] = pack_bf16x2(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1]));
+      }
+    }
+    uint4* d1 = reinterpret_cast<uint4*>(dst + c * 16);
+    uint4* d2 = reinterpret_cast<uint4*>(dst + 64 + c * 16);
+    d1[0] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+    d1[1] = make_uint4(w1[4], w1[5], w1[6], w1[7]);
+    d2[0] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+    d2[1] = make_uint4(w2[4], w2[5], w2[6], w2[7]);
+  }
+}
+
 // Tile rasterisation: bands of group_m m-tiles, m fastest inside a band.  The CTAs running at any
 // moment then share ~group_m A tiles and only ~(#CTAs / group_m) weight tiles, so the working set
 // stays inside the 126 MB L2 even for the 180 MB Llama gate/up weight (n-fastest order re-read the
@@ -241,7 +305,7 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
   n = r / gm;
 }
 
-template <int BN, int CTAS>
+template <int BN, int CTAS, bool ROPE = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
@@ -424,8 +488,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         out_row = (long long)(m / epi.row_period) * epi.remap_stride + epi.remap_offset +
                   (m % epi.row_period);
       const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-      epilogue_chunks(t_row, epi, bias_s, m, out_row, row_ok, n_base, N, half == 0 ? 0 : NCH0,
-                      half == 0 ? NCH0 : NCH);
+      if constexpr (ROPE) {
+        // BN = 256: this warp's half of the tile is one 128-wide head
+        epilogue_rope_head(t_row + half * 128, epi, m, row_ok, n_base + half * 128);
+      } else {
+        epilogue_chunks(t_row, epi, bias_s, m, out_row, row_ok, n_base, N, half == 0 ? 0 : NCH0,
+                        half == 0 ? NCH0 : NCH);
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
@@ -491,13 +560,13 @@ struct GemmProfRec { cudaEvent_t e0, e1; int M, N, K; };
 static std::deque<GemmProfRec> g_prof;
 static bool g_prof_on = false;
 
-template <int BN, int CTAS>
+template <int BN, int CTAS, bool ROPE = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                        const EpiParams& epi, int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTAS>;
   static bool configured = false;
   if (!configured) {
-    CGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS>,
+    CGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS, ROPE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
@@ -517,7 +586,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS>, ta, tb, M, N, K, epi));
+  CGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS, ROPE>, ta, tb, M, N, K, epi));
   ++g_gemm_launches;
   return 0;
 }
@@ -558,6 +627,20 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   p.red_inplace = (p.resid != nullptr && p.resid == p.out && p.out_f32 && p.resid_f32 && p.ldr == p.ldo &&
                    p.act == CGPT_ACT_NONE && p.row_add == nullptr && !getenv("CGPT_GEMM_NO_RED")) ? 1 : 0;
   p.dbg = reinterpret_cast<long long*>(getenv("CGPT_GEMM_DBG") ? strtoull(getenv("CGPT_GEMM_DBG"), nullptr, 0) : 0ull);
+  const cgpt_gemm_rope* rp = e->rope;
+  if (rp != nullptr) {
+    CGPT_REQUIRE(rp->heads > 0 && N == 3 * rp->heads * 128, "gemm(rope): N = %d must be 3 * heads * 128 (heads = %d)", N, rp->heads);
+    CGPT_REQUIRE(!p.out_f32 && p.bias == nullptr && p.resid == nullptr && p.act == CGPT_ACT_NONE && p.row_add == nullptr &&
+                     p.remap_stride == 0,
+                 "gemm(rope): the fused QKV epilogue takes bf16 out and no bias / residual / activation / remap");
+    CGPT_REQUIRE(rp->T > 0 && M % rp->T == 0 && rp->cos_table && rp->sin_table && rp->kcache && rp->vcache &&
+                     rp->ld_cache % 8 == 0 && p.ldo % 8 == 0 && rp->cache_row0 + rp->T <= rp->cache_rows_per_batch,
+                 "gemm(rope): bad rope / cache arguments (M = %d, T = %d)", M, rp->T);
+    p.rope_T = rp->T; p.rope_pos0 = rp->pos0; p.rope_hidden = rp->heads * 128;
+    p.rope_cos = rp->cos_table; p.rope_sin = rp->sin_table;
+    p.rope_k = reinterpret_cast<__nv_bfloat16*>(rp->kcache); p.rope_v = reinterpret_cast<__nv_bfloat16*>(rp->vcache);
+    p.rope_ldc = rp->ld_cache; p.rope_cache_rows = rp->cache_rows_per_batch; p.rope_cache_row0 = rp->cache_row0;
+  }
   CGPT_REQUIRE(p.row_add == nullptr || p.row_period > 0, "gemm: row_add needs row_period > 0");
   CGPT_REQUIRE(p.act != CGPT_ACT_SWIGLU || (!p.out_f32 && p.resid == nullptr && p.row_add == nullptr),
                "gemm: SwiGLU epilogue writes bf16 and takes no residual");
@@ -594,6 +677,11 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
     }
   }
   int rc = 0;
+  if (rp != nullptr) {
+    CGPT_REQUIRE(bn == 256, "gemm(rope): needs 256-wide N tiles (got %d)", bn);
+    rc = ctas == 2 ? launch_gemm<256, 2, true>(ta, tb, M, N, K, p, e->max_ctas, stream)
+                   : launch_gemm<256, 1, true>(ta, tb, M, N, K, p, e->max_ctas, stream);
+  } else
   switch (bn * 10 + ctas) {
     case 2561: rc = launch_gemm<256, 1>(ta, tb, M, N, K, p, e->max_ctas, stream); break;
     case 1761: rc = launch_gemm<176, 1>(ta, tb, M, N, K, p, e->max_ctas, stream); break;

@@ -18,6 +18,7 @@ of libcgpt.so.  One call of `noisy_labels` = one batch of the reference's hot lo
 The residual streams are fp32, GEMM operands bf16, accumulation fp32.
 """
 import math
+import os
 
 import torch
 
@@ -275,9 +276,15 @@ class MiniGPT4Engine:
         for i in range(l.layers):
             o = f"llm.{i}."
             L.norm_rows(res, w[o + "n1"], None, l.rms_eps, xn, rms=True)
-            L.gemm(xn, w[o + "qkv.w"], out=qkv)
-            L.rope_split(qkv, T, l.heads, l.head_dim, pos0, w["rope.cos"], w["rope.sin"], kc[i], vc[i],
-                         cache_rows, cache_row0)
+            if l.head_dim == 128 and not os.environ.get("CGPT_NO_FUSED_ROPE"):
+                # rotary embedding + KV-cache append inside the QKV GEMM's epilogue
+                L.gemm(xn, w[o + "qkv.w"], out=qkv,
+                       rope=dict(T=T, heads=l.heads, pos0=pos0, cos=w["rope.cos"], sin=w["rope.sin"], kcache=kc[i],
+                                 vcache=vc[i], cache_rows=cache_rows, cache_row0=cache_row0))
+            else:
+                L.gemm(xn, w[o + "qkv.w"], out=qkv)
+                L.rope_split(qkv, T, l.heads, l.head_dim, pos0, w["rope.cos"], w["rope.sin"], kc[i], vc[i],
+                             cache_rows, cache_row0)
             Tk = cache_row0 + T
             L.attention(qkv[:, :Hd], kc[i].view(-1, Hd), vc[i].view(-1, Hd), att, B=B, H=l.heads, Tq=T, Tk=Tk,
                         head_dim=l.head_dim, scale=scale, kv_rows_per_batch=cache_rows, causal=True, decode=decode)

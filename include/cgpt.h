@@ -46,6 +46,20 @@ long long cgpt_launch_count(void);
  * Replaces every nn.Linear / patch Conv2d on the path: eva_vit.py:202 (PatchEmbed.proj),
  * :126-131 (qkv), :151 (proj), :60-64 (fc1/fc2); Qformer.py:128-135,285-289,358-375;
  * minigpt4.py:76-78,141 (llama_proj); HF LlamaForCausalLM q/k/v/o/gate/up/down/lm_head. */
+/* optional fused tail of a fused QKV projection with 128-wide heads (HF LlamaAttention: q/k/v_proj, rotary
+ * embedding, KV-cache update): N = 3*heads*128; q (rotated) goes to columns [0, heads*128) of `out`, rotated k
+ * and plain v go to the KV cache row b*cache_rows_per_batch + cache_row0 + i of row m = b*T + i (position pos0 + i).
+ * Replaces the separate cgpt_rope_split pass. */
+typedef struct cgpt_gemm_rope {
+  int T, heads, pos0;
+  const float* cos_table;   /* fp32 [max_pos, 64] */
+  const float* sin_table;
+  void* kcache;
+  void* vcache;
+  int64_t ld_cache;
+  int cache_rows_per_batch, cache_row0;
+} cgpt_gemm_rope;
+
 typedef struct cgpt_gemm_epilogue {
   void* out;            /* [rows, ldo] bf16 or f32                                          */
   int64_t ldo;          /* elements                                                         */
@@ -62,6 +76,7 @@ typedef struct cgpt_gemm_epilogue {
   int remap_stride;     /* >0: out row = (m / row_period) * remap_stride + remap_offset + m % row_period */
   int remap_offset;
   int max_ctas;         /* 0 = one persistent CTA per SM                                    */
+  const cgpt_gemm_rope* rope; /* NULL, or the fused rotary + KV-cache-append tail (see above)     */
 } cgpt_gemm_epilogue;
 
 int cgpt_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,

@@ -80,3 +80,51 @@ def test_gemm_rejects_bad_shapes(lib):
     w = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(lib.CgptError):
         lib.gemm(a, w)
+
+
+@pytest.mark.parametrize("B,T,heads,pos0,row0,rows", [(3, 72, 4, 7, 7, 83), (40, 1, 4, 80, 80, 83), (5, 7, 32, 0, 0, 7),
+                                                      (130, 5, 2, 3, 9, 20)])
+def test_fused_rope_kv_append_epilogue_matches_separate_pass(lib, B, T, heads, pos0, row0, rows):
+    """QKV GEMM with the fused rotary + KV-cache-append epilogue vs plain GEMM + cgpt_rope_split and vs an fp32
+    torch restatement of HF's apply_rotary_pos_emb (rotate_half).  The fused path rotates the fp32 accumulators
+    (one rounding), the separate pass rotates bf16-rounded values (two roundings): compare both to the fp32 truth."""
+    hd, K = 128, 256
+    D = heads * hd
+    g = torch.Generator(device="cuda").manual_seed(T + heads)
+    x = torch.randn(B * T, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(3 * D, K, device="cuda", generator=g) * 0.08).bfloat16()
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+    fr = torch.outer(torch.arange(256, dtype=torch.float32), inv)
+    cos_t, sin_t = fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+
+    def fresh():
+        return (torch.full((B, rows, D), 7.0, device="cuda").bfloat16(), torch.full((B, rows, D), -3.0, device="cuda").bfloat16(),
+                torch.zeros(B * T, 3 * D, device="cuda", dtype=torch.bfloat16))
+
+    kc1, vc1, q1 = fresh()
+    lib.gemm(x, w, out=q1, rope=dict(T=T, heads=heads, pos0=pos0, cos=cos_t, sin=sin_t, kcache=kc1, vcache=vc1,
+                                     cache_rows=rows, cache_row0=row0))
+    kc2, vc2, q2 = fresh()
+    lib.gemm(x, w, out=q2)
+    lib.rope_split(q2, T, heads, hd, pos0, cos_t, sin_t, kc2, vc2, rows, row0)
+    torch.cuda.synchronize()
+    # fp32 truth
+    y = (x.float() @ w.float().t()).view(B, T, 3, heads, hd)
+    pos = pos0 + torch.arange(T, device="cuda")
+    c = torch.cat([cos_t[pos], cos_t[pos]], -1)[None, :, None, :]
+    s_ = torch.cat([sin_t[pos], sin_t[pos]], -1)[None, :, None, :]
+    rot = lambda t: torch.cat([-t[..., hd // 2:], t[..., :hd // 2]], -1)
+    q_ref = y[:, :, 0] * c + rot(y[:, :, 0]) * s_
+    k_ref = y[:, :, 1] * c + rot(y[:, :, 1]) * s_
+    v_ref = y[:, :, 2]
+    scale = max(1.0, y.abs().max().item())
+    for got_q, got_k, got_v, tol in [(q1, kc1, vc1, 1e-2), (q2, kc2, vc2, 2e-2)]:
+        assert (got_q[:, :D].float().view(B, T, heads, hd) - q_ref).abs().max().item() < tol * scale
+        assert (got_k[:, row0:row0 + T].float().view(B, T, heads, hd) - k_ref).abs().max().item() < tol * scale
+        assert (got_v[:, row0:row0 + T].float().view(B, T, heads, hd) - v_ref).abs().max().item() < tol * scale
+    # cache rows outside [row0, row0 + T) untouched
+    keep = torch.ones(rows, dtype=torch.bool)
+    keep[row0:row0 + T] = False
+    assert (kc1[:, keep] == 7.0).all() and (vc1[:, keep] == -3.0).all()
+    # v is a plain copy in both paths: bit-identical
+    assert torch.equal(vc1[:, row0:row0 + T], vc2[:, row0:row0 + T])
