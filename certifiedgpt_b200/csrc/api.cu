@@ -90,6 +90,11 @@ int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int3
                       (cudaStream_t)stream);
 }
 
+int cgpt_ce_loss(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, float* token_loss,
+                 float* mean_count, void* stream) {
+  return ce_loss(logits, ld, rows, cols, targets, token_loss, mean_count, (cudaStream_t)stream);
+}
+
 int cgpt_cosine_rows(const float* feats, int64_t ld, int rows, int D, const float* target, float* scores,
                      void* stream) {
   return cosine_rows(feats, ld, rows, D, target, scores, (cudaStream_t)stream);

@@ -975,6 +975,51 @@ int cgpt_llm_prefill_decode(cgpt_handle E, const void* queries, int B, int32_t* 
   return 0;
 }
 
+// clamp(ids, 0): -100 (ignored target) -> pad id 0 for the embedding lookup
+__global__ void clamp_ids_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int n, int pad_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] < 0 ? pad_id : src[i];
+}
+
+int cgpt_lm_loss(cgpt_handle E, const void* patches, int B, const int32_t* answer_ids, int na, float* out_token_loss,
+                 float* out_mean_count, void* stream) {
+  CGPT_REQUIRE(E && patches && answer_ids && out_token_loss, "cgpt_lm_loss: null argument");
+  const cgpt_model_config& c = E->c;
+  CGPT_REQUIRE(na >= 1 && na <= c.max_new_tokens, "cgpt_lm_loss: %d answer tokens, the KV cache holds %d", na, c.max_new_tokens);
+  const int Tl = E->Tp + na;                                   // rows per sample: image + suffix + answer
+  const long long max_b1 = static_cast<long long>(E->ws_B) * E->Tp / Tl, max_b2 = E->ws_B / na;
+  CGPT_TRY(check_ready(E, 1, true));
+  CGPT_REQUIRE(B >= 1 && B <= max_b1 && B <= max_b2 && B * na <= E->ws_B,
+               "cgpt_lm_loss: batch %d too large for the bound workspace (max %lld)", B, max_b1 < max_b2 ? max_b1 : max_b2);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Buffers& b = E->b;
+  const int nq = c.qf_queries, P = E->P, Hd = c.llm_hidden, ns = E->ns;
+  const int M = B * Tl;
+  const long long layer_stride = static_cast<long long>(E->ws_B) * E->cache_rows * Hd;
+  CGPT_TRY(vit_forward(E, patches, B, b.v_out, s));
+  CGPT_TRY(qformer_forward(E, b.v_out, B, b.q_h, s));
+  // [image | suffix | answer] rows of every sample
+  CGPT_TRY(gemm(b.q_h, c.qf_hidden, E->proj_w, B * nq, Hd, c.qf_hidden,
+                Epi(b.l_res, Hd, CGPT_DT_F32).bias(E->proj_b).remap(nq, Tl, 0), s));
+  if (ns > 0)
+    CGPT_TRY(gather_rows(E->emb, Hd, E->suffix_ids, ns, B * ns, Hd, b.l_res, Hd, CGPT_DT_F32, ns, Tl, nq, s));
+  int32_t* ids = b.ids;                                        // [B*na] <= ws_B * max_new_tokens
+  clamp_ids_kernel<<<(B * na + 255) / 256, 256, 0, s>>>(answer_ids, ids, B * na, c.pad_id);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  CGPT_TRY(gather_rows(E->emb, Hd, ids, B * na, B * na, Hd, b.l_res, Hd, CGPT_DT_F32, na, Tl, nq + ns, s));
+  // the KV cache has P + Tp + max_new rows per sample: rows [P, P + Tl) are (re)written here
+  CGPT_TRY(llm_layers(E, M, Tl, B, b.l_res, b.l_xn, b.l_qkv, b.l_att, b.l_act, b.kc, b.vc, layer_stride, P, P,
+                      E->cache_rows, 0, s));
+  // position (nq + ns - 1 + j) predicts answer token j: final norm + lm_head on those B*na rows only
+  CGPT_TRY(norm_rows(b.l_res, Hd, CGPT_DT_F32, E->llm_norm, nullptr, c.llm_rms_eps, B * na, Hd, b.l_xn, Hd, CGPT_DT_BF16, 1,
+                     na, Tl, nq + ns - 1, s));
+  CGPT_TRY(gemm(b.l_xn, Hd, E->head_w, B * na, c.llm_vocab, Hd, Epi(b.l_logits, c.llm_vocab, CGPT_DT_F32), s));
+  CGPT_TRY(ce_loss(static_cast<const float*>(b.l_logits), c.llm_vocab, B * na, c.llm_vocab, answer_ids, out_token_loss,
+                   out_mean_count, s));
+  return 0;
+}
+
 int cgpt_noisy_labels(cgpt_handle E, const float* x, const cgpt_noise_spec* noise, uint64_t first_sample, int B,
                       int32_t* labels, void* stream) {
   CGPT_REQUIRE(E && x && noise && labels, "cgpt_noisy_labels: null argument");

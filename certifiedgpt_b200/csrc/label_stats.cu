@@ -408,4 +408,77 @@ int cosine_rows(const float* feats, long long ld, int rows, int D, const float* 
   return 0;
 }
 
+
+// ------------------------------------------------------------------ language-model loss (modeling_llama.py:101-123)
+// loss[r] = logsumexp(logits[r, :]) - logits[r, target[r]]  (fp32; 0 and not counted when target[r] < 0 = ignore_index)
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ logits, long long ld, int cols,
+                                                      const int* __restrict__ targets, float* __restrict__ loss) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  const int t = targets[r];
+  if (t < 0 || t >= cols) {          // uniform per block
+    if (threadIdx.x == 0) loss[r] = 0.f;
+    return;
+  }
+  const float* row = logits + r * ld;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, row[c]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) sum += expf(row[c] - mx);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];   // fixed order
+    loss[r] = logf(tot) + mx - row[t];
+  }
+}
+// out[0] = mean of loss[r] over targets[r] >= 0 (CrossEntropyLoss reduction='mean'), out[1] = their count.
+// One block, fixed summation order: the result does not depend on scheduling.
+__global__ void __launch_bounds__(256) masked_mean_kernel(const float* __restrict__ loss, const int* __restrict__ targets,
+                                                          int rows, int cols, float* __restrict__ out) {
+  __shared__ double s_sum[256];
+  __shared__ int s_cnt[256];
+  double acc = 0.0;
+  int cnt = 0;
+  for (int r = threadIdx.x; r < rows; r += 256) {
+    const int t = targets[r];
+    if (t >= 0 && t < cols) { acc += static_cast<double>(loss[r]); ++cnt; }
+  }
+  s_sum[threadIdx.x] = acc;
+  s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s_sum[threadIdx.x] += s_sum[threadIdx.x + o]; s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = s_cnt[0] > 0 ? static_cast<float>(s_sum[0] / s_cnt[0]) : 0.f;
+    out[1] = static_cast<float>(s_cnt[0]);
+  }
+}
+
+int ce_loss(const float* logits, long long ld, int rows, int cols, const int* targets, float* token_loss,
+            float* mean_count, cudaStream_t stream) {
+  CGPT_REQUIRE(logits && targets && token_loss && rows > 0 && cols > 0, "ce_loss: bad arguments rows=%d cols=%d", rows, cols);
+  ce_rows_kernel<<<rows, 256, 0, stream>>>(logits, ld, cols, targets, token_loss);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  if (mean_count != nullptr) {
+    masked_mean_kernel<<<1, 256, 0, stream>>>(token_loss, targets, rows, cols, mean_count);
+    CGPT_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return 0;
+}
+
 }  // namespace cgpt

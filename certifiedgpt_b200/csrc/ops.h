@@ -36,6 +36,8 @@ int certify_tail(const long long* counts_sel, const long long* counts_est, int n
                  double alpha, double sigma, int* out_label, double* out_stats, cudaStream_t stream);
 int predict_tail(const long long* counts, int num_classes, double alpha, int* out_label,
                  double* out_stats, cudaStream_t stream);
+int ce_loss(const float* logits, long long ld, int rows, int cols, const int* targets, float* token_loss,
+            float* mean_count, cudaStream_t stream);
 int cosine_rows(const float* feats, long long ld, int rows, int D, const float* target, float* scores,
                 cudaStream_t stream);
 int norm_rows(const void* x, long long ldx, int in_dtype, const float* gamma, const float* beta,

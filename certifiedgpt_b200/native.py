@@ -61,6 +61,7 @@ def _declare(lib):
         "cgpt_qformer_forward": [vp, vp, i32, vp, vp, vp],
         "cgpt_llm_prefill_decode": [vp, vp, i32, vp, vp, C.POINTER(i32), vp],
         "cgpt_noisy_labels": [vp, vp, pns, u64, i32, vp, vp],
+        "cgpt_lm_loss": [vp, vp, i32, vp, i32, vp, vp, vp],
         "cgpt_sample_noise": [vp, vp, pns, i64, i64, i32, i64, i32, i32, vp, vp, vp, vp],
         "cgpt_certify": [vp, vp, pns, i64, i64, f64, i32, i32, i32, vp, C.POINTER(i32), C.POINTER(f64),
                          C.POINTER(f64), vp],
@@ -385,6 +386,30 @@ class NativeMiniGPT4Engine:
                                                   C.byref(steps), L.stream_ptr()))
         self.last_steps = steps.value
         return ids, margin, steps.value
+
+    @torch.no_grad()
+    def lm_loss(self, images, answers, noise_level=0.0, *, noise_kind=L.NOISE_UNIFORM, noise_space=L.SPACE_NORMALIZED,
+                seed=0, step=0, mean=L.BLIP_MEAN, std=L.BLIP_STD):
+        """Teacher-forced LM loss of the fine-tune / validation forward (MiniGPTBase.forward, minigpt_base.py:323-362;
+        modeling_llama.py:101-123) for B different images [B,3,S,S] with answers [B, na] (int, -100 = padding).
+        Noise as in MiniGPT4FineTuneAgent.maybe_add_noise (agents/minigpt4_finetune_agent.py:142-148:
+        image + rand_like(image) * noise_level), drawn by K1 with Philox key (seed, step, image index).
+        Returns (mean loss over answer tokens, per-token losses [B, na]); forward only."""
+        B, na = answers.shape
+        v = self.cfg.vit
+        assert tuple(images.shape) == (B, 3, v.img_size, v.img_size) and images.is_cuda
+        self.reserve(max(B * max(na, 2), self._ws_B))
+        G2 = v.grid * v.grid
+        patches = torch.empty(B * G2, 592, dtype=torch.bfloat16, device=self.dev)
+        for b in range(B):      # a different image per row: one K1 launch each (training batches are small)
+            L.noise_patchify(images[b].float().contiguous(), 1, float(noise_level), seed=seed, stream_id=step, first_sample=b,
+                             noise_space=noise_space, noise_kind=noise_kind, mean=mean, std=std,
+                             out=patches[b * G2:(b + 1) * G2])
+        ans = answers.to(device=self.dev, dtype=torch.int32).contiguous()
+        tok = torch.empty(B * na, dtype=torch.float32, device=self.dev)
+        mc = torch.empty(2, dtype=torch.float32, device=self.dev)
+        L.check(self._lib.cgpt_lm_loss(self._h, L.ptr(patches), B, L.ptr(ans), na, L.ptr(tok), L.ptr(mc), L.stream_ptr()))
+        return mc[0], tok.view(B, na)
 
     @torch.no_grad()
     def encode_noisy(self, x, B, sigma, *, seed=0, stream_id=0, first_sample=0, noise_space=L.SPACE_NORMALIZED,

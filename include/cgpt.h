@@ -138,6 +138,12 @@ int cgpt_certify_tail(const int64_t* counts_sel, const int64_t* counts_est, int 
 int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int32_t* out_label,
                       double* out_stats, void* stream);
 
+/* token_loss[r] = logsumexp(logits[r, :]) - logits[r, targets[r]] in fp32, 0 where targets[r] < 0 (ignore_index
+ * -100); mean_count (nullable) = {mean over the counted rows, their number} by a fixed-order reduction.
+ * CrossEntropyLoss(reduction='mean') of the training / validation forward (modeling_llama.py:101-123). */
+int cgpt_ce_loss(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, float* token_loss,
+                 float* mean_count, void* stream);
+
 /* scores[r] = cos(feats[r, :], target) in fp32 (one warp per row): the CLIP feature cosine of the black-box
  * attack loop (BASELINE.json configs[4]; README.md:62-64 - the reference ships no code for it) */
 int cgpt_cosine_rows(const float* feats, int64_t ld, int rows, int D, const float* target, float* scores,
@@ -262,6 +268,15 @@ int cgpt_qformer_forward(cgpt_handle h, const void* tokens, int B, void* out_que
  * steps only when early_exit is set. */
 int cgpt_llm_prefill_decode(cgpt_handle h, const void* queries, int B, int32_t* out_ids, float* out_top2_margin,
                             int* out_steps, void* stream);
+/* Teacher-forced language-model loss of the fine-tune / validation forward (MiniGPTBase.forward,
+ * minigpt_base.py:323-362; loss modeling_llama.py:101-123): B DIFFERENT images, already noised and patchified by
+ * the caller (patches bf16 [B*G*G, 592]; agents/minigpt4_finetune_agent.py:142-148 adds uniform noise), go through
+ * ViT -> Q-Former -> llama_proj; the sequence [prefix | image | suffix | answer] runs through the frozen Llama and the
+ * answer tokens are scored.  answer_ids: device int32 [B, na], -100 = padding (ignored); na <= max_new_tokens.
+ * out_token_loss: device f32 [B*na]; out_mean_count: device f32 [2] = {mean loss over scored tokens, their count}.
+ * Forward only: the backward pass for the llama_proj gradient is not part of this library yet. */
+int cgpt_lm_loss(cgpt_handle h, const void* patches, int B, const int32_t* answer_ids, int na, float* out_token_loss,
+                 float* out_mean_count, void* stream);
 /* one batch of the hot loop: labels[b] = class of f(x + sigma * eps_{first_sample + b}), b < B.
  * x: fp32 [3,S,S] device pointer.  labels: device int32 [B]. */
 int cgpt_noisy_labels(cgpt_handle h, const float* x, const cgpt_noise_spec* noise, uint64_t first_sample, int B,

@@ -218,6 +218,28 @@ def generate_ids(sd, cfg, embeds, max_new_tokens=20, min_length=1, prefix="llama
 
 
 # ------------------------------------------------------------------ answer -> label adapter
+def lm_loss(sd, cfg, images, prefix_ids, suffix_ids, answers, prefix="llama_model."):
+    """Training / validation forward of MiniGPTBase (minigpt_base.py:323-362): inputs = [bos+prompt | image | rest of
+    the prompt | answer], targets = answer ids at the answer positions and -100 elsewhere, loss = the shifted
+    CrossEntropyLoss(mean) of modeling_llama.py:101-123.  answers: LongTensor [B, na], -100 = right padding
+    (pad embedding fed, target ignored).  Returns (mean loss, per-token losses [B, na])."""
+    l = cfg.llm
+    emb = sd[prefix + "model.embed_tokens.weight"]
+    img = encode_img(sd, cfg, images)
+    cond = build_prompt_embeds(sd, cfg, img, prefix_ids, suffix_ids, prefix=prefix)
+    ans_in = answers.clamp_min(0).masked_fill(answers < 0, l.pad_id)
+    embeds = torch.cat((cond, emb[ans_in].float()), dim=1)
+    hidden, _ = llama_forward(sd, cfg, embeds, prefix=prefix)
+    logits = F.linear(hidden, sd[prefix + "lm_head.weight"]).float()
+    Lc, na = cond.shape[1], answers.shape[1]
+    targets = torch.full(embeds.shape[:2], -100, dtype=torch.long)
+    targets[:, Lc:Lc + na] = answers
+    shift_logits, shift_labels = logits[:, :-1].reshape(-1, l.vocab), targets[:, 1:].reshape(-1)
+    loss = F.cross_entropy(shift_logits, shift_labels, ignore_index=-100, reduction="mean")
+    tok = F.cross_entropy(shift_logits, shift_labels, ignore_index=-100, reduction="none").view(embeds.shape[0], -1)
+    return loss, tok[:, Lc - 1:Lc - 1 + na]
+
+
 def canonical_answer(ids, eos_id=2):
     """Token-level restatement of minigpt_base.py:438-446: decode(skip_special_tokens=True) drops
     <unk>=0,<s>=1,</s>=2; everything after the first EOS is padding."""

@@ -105,6 +105,18 @@ def test_448px_path_matches_oracle():
         mo.encode_img(sd, cfg, images, collect=ref)
     for k in ("embed", "block1", "image_embeds", "layer1"):
         assert _rel(got[k], ref[k]) < 2e-2, k
+    # the native engine at 448 px: per-subsystem entry points bit-identical to the Python-driven kernels, and the
+    # whole noisy batch gives the same labels
+    from certifiedgpt_b200 import _lib as L
+    from certifiedgpt_b200.native import NativeMiniGPT4Engine
+    nat = NativeMiniGPT4Engine.from_engine(eng)
+    patches = torch.cat([L.noise_patchify(images[b].cuda().contiguous(), 1, 0.0) for b in range(2)])
+    tokens = nat.vit_forward(patches)
+    queries, _ = nat.qformer_forward(tokens)
+    assert torch.equal(tokens.float().cpu(), got["image_embeds"].cpu())
+    assert torch.equal(queries.float().cpu(), got["qformer"].cpu())
+    x = torch.rand(3, 448, 448, generator=torch.Generator().manual_seed(6)).cuda()
+    assert torch.equal(nat.noisy_labels(x, 3, 0.25, seed=4).cpu(), eng.noisy_labels(x, 3, 0.25, seed=4).cpu())
 
 
 def test_full_width_llm_matches_oracle():

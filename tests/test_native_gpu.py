@@ -223,3 +223,51 @@ def test_gemm_profile_hook_counts_eager_launches():
     expect = (1 + 4 * v.depth) + (1 + q.layers * 4 + n_cross * 2) + 1 + nat.last_steps * (4 * l.layers + 1)
     assert len(rec) == expect
     assert all(ms >= 0 and fl > 0 for ms, fl, _ in rec)
+
+
+@pytest.mark.parametrize("name,cfg", [("tiny", ModelConfig.tiny()), ("wide", WIDE)])
+def test_lm_loss_forward_matches_oracle(name, cfg):
+    """cgpt_lm_loss (validation / fine-tune forward, teacher forcing + shifted CE) vs the fp32 oracle, clean and with
+    the fine-tune agent's uniform noise (noise regenerated on the host side from the same Philox draws)."""
+    from certifiedgpt_b200 import _lib as L
+    sd, py, nat, _ = _setup(cfg, seed=31, max_new=4)
+    S = cfg.vit.img_size
+    B = 5
+    images = torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(2))
+    V = cfg.llm.vocab
+    answers = torch.tensor([[7, 9, 2, -100], [11, 2, -100, -100], [V - 1, 5, 6, 2], [3, 2, -100, -100], [8, 8, 8, 2]])
+    loss, tok = nat.lm_loss(images.cuda(), answers, 0.0)
+    ref_loss, ref_tok = mo.lm_loss(sd, cfg, images, py.prefix_ids, py.suffix_ids, answers)
+    assert abs(loss.item() - ref_loss.item()) < 2e-2 * max(1.0, ref_loss.item())
+    assert (tok.cpu() - ref_tok).abs().max().item() < 5e-2 * max(1.0, ref_tok.max().item())
+    assert (tok.cpu()[answers < 0] == 0).all()
+    # uniform noise: image + U[0,1) * level, keyed by (seed, step, image index)
+    lvl = 0.25
+    loss_n, _ = nat.lm_loss(images.cuda(), answers, lvl, seed=3, step=5)
+    noisy = torch.stack([L.noise_image(images[b].cuda().contiguous(), 1, lvl, seed=3, stream_id=5, first_sample=b,
+                                       noise_kind=L.NOISE_UNIFORM)[0] for b in range(B)]).cpu()
+    assert (noisy - images).min() >= 0 and (noisy - images).max() < lvl
+    ref_n, _ = mo.lm_loss(sd, cfg, noisy, py.prefix_ids, py.suffix_ids, answers)
+    assert abs(loss_n.item() - ref_n.item()) < 2e-2 * max(1.0, ref_n.item())
+    # the generate path still works afterwards (the loss pass wrote answer K/V into the cache rows decode reuses)
+    x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(3)).cuda()
+    assert torch.equal(nat.noisy_labels(x, 4, 0.5, seed=1).cpu(), py.noisy_labels(x, 4, 0.5, seed=1).cpu())
+
+
+def test_ce_loss_kernel_matches_torch():
+    from certifiedgpt_b200 import _lib as L
+    from certifiedgpt_b200 import native as N
+    import ctypes as C
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(37, 32000, generator=g) * 4
+    tg = torch.randint(0, 32000, (37,), generator=g)
+    tg[5], tg[20] = -100, -100
+    lg, tgd = logits.cuda(), tg.int().cuda()
+    tok = torch.empty(37, device="cuda")
+    mc = torch.empty(2, device="cuda")
+    h = N.lib()
+    h.cgpt_ce_loss.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.check(h.cgpt_ce_loss(L.ptr(lg), lg.stride(0), 37, 32000, L.ptr(tgd), L.ptr(tok), L.ptr(mc), L.stream_ptr()))
+    ref = torch.nn.functional.cross_entropy(logits.double(), tg, ignore_index=-100, reduction="none")
+    assert (tok.cpu().double() - ref).abs().max().item() < 1e-4
+    assert abs(mc[0].item() - ref.sum().item() / 35) < 1e-4 and mc[1].item() == 35

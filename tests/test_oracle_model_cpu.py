@@ -110,3 +110,27 @@ def test_pos_embed_interpolation_matches_reference():
     cfg.vit.img_size = 112                       # 8x8 patches + cls = 65 tokens
     sd = import_state_dicts(cfg, vit_sd={"pos_embed": ref["in"], "cls_token": torch.zeros(1, 1, 16)})
     assert torch.equal(sd["visual_encoder.pos_embed"], ref["out"]) and "visual_encoder.cls_token" in sd
+
+
+def test_lm_loss_matches_hf_causal_lm_loss():
+    """oracle.lm_loss (the restated training forward, minigpt_base.py:323-362 + modeling_llama.py:101-123) equals
+    transformers' LlamaForCausalLM(inputs_embeds, labels).loss on the same embeddings, padding included."""
+    cfg = ModelConfig.tiny()
+    sd = random_state_dict(cfg, seed=9)
+    hf = _hf_llama(cfg, sd)
+    S = cfg.vit.img_size
+    images = torch.randn(3, 3, S, S, generator=torch.Generator().manual_seed(4))
+    prefix, suffix = (1, 5, 6), (7, 8, 9, 10)
+    answers = torch.tensor([[11, 12, 2], [13, 2, -100], [14, 15, 16]])
+    loss, tok = mo.lm_loss(sd, cfg, images, prefix, suffix, answers)
+    with torch.no_grad():
+        img = mo.encode_img(sd, cfg, images)
+        cond = mo.build_prompt_embeds(sd, cfg, img, prefix, suffix)
+        emb = sd["llama_model.model.embed_tokens.weight"]
+        embeds = torch.cat((cond, emb[answers.clamp_min(0)]), dim=1)
+        labels = torch.full(embeds.shape[:2], -100, dtype=torch.long)
+        labels[:, cond.shape[1]:] = answers
+        ref = hf(inputs_embeds=embeds, labels=labels).loss
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert tok.shape == (3, 3) and tok[1, 2].item() == 0.0 and (tok[answers >= 0] > 0).all()
+    assert abs(tok.sum().item() / 8 - loss.item()) < 1e-5
