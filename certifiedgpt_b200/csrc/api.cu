@@ -120,4 +120,44 @@ int cgpt_gather_rows(const void* table, int64_t ldt, const int32_t* ids, int id_
                      remap_offset, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------- fine-tune step kernels
+int cgpt_swiglu_fwd(const void* gu, void* act, int64_t rows, int inter, void* stream) {
+  return swiglu_fwd(gu, act, rows, inter, (cudaStream_t)stream);
+}
+int cgpt_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int inter, void* stream) {
+  return swiglu_bwd(gu, dact, dgu, rows, inter, (cudaStream_t)stream);
+}
+int cgpt_rmsnorm_bwd(const float* x, int64_t ldx, const float* gamma, const float* dy, int64_t ldy, float eps, int rows, int D,
+                     float* dx, int64_t lddx, int row_period, int row_stride, int row_offset, void* stream) {
+  return rmsnorm_bwd(x, ldx, gamma, dy, ldy, eps, rows, D, dx, lddx, row_period, row_stride, row_offset, (cudaStream_t)stream);
+}
+int cgpt_rope_bwd_cast(const float* dqkv, void* out, int rows, int T, int H, int head_dim, int pos0, const float* cos_table,
+                       const float* sin_table, void* stream) {
+  return rope_bwd_cast(dqkv, out, rows, T, H, head_dim, pos0, cos_table, sin_table, (cudaStream_t)stream);
+}
+int cgpt_attention_bwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, int64_t ld_cache,
+                       int cache_rows_per_batch, const void* o, int64_t ldo, const void* dout, int64_t lddo, float* dqkv,
+                       int B, int H, int head_dim, int Tq, int Tk, float scale, void* stream) {
+  return attention_bwd(q, ldq, kcache, vcache, ld_cache, cache_rows_per_batch, o, ldo, dout, lddo, dqkv, B, H, head_dim, Tq,
+                       Tk, scale, (cudaStream_t)stream);
+}
+int cgpt_ce_grad(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, const float* mean_count,
+                 void* dlogits, int64_t ldd, void* stream) {
+  return ce_grad(logits, ld, rows, cols, targets, mean_count, dlogits, ldd, (cudaStream_t)stream);
+}
+int cgpt_cast_rows_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, int row_period,
+                            int row_stride, int row_offset, void* stream) {
+  return cast_rows_f32_bf16(src, lds, dst, ldd, rows, cols, row_period, row_stride, row_offset, (cudaStream_t)stream);
+}
+int cgpt_transpose_bf16(const void* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream) {
+  return transpose_bf16(src, lds, dst, ldd, rows, cols, (cudaStream_t)stream);
+}
+int cgpt_colsum_bf16(const void* src, int64_t lds, int rows, int cols, float* out, void* stream) {
+  return colsum_bf16(src, lds, rows, cols, out, (cudaStream_t)stream);
+}
+int cgpt_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  return adamw_step(p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream);
+}
+
 }  // extern "C"

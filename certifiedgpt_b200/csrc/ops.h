@@ -54,4 +54,22 @@ int rope_split(void* qkv, long long ld, int rows, int T, int H, int head_dim, in
 int gather_rows(const void* table, long long ldt, const int* ids, int id_period, int rows, int D, void* out,
                 long long ldo, int out_dtype, int remap_period, int remap_stride, int remap_offset,
                 cudaStream_t stream);
+// fine-tune step (train_ops.cu)
+int swiglu_fwd(const void* gu, void* act, long long rows, int inter, cudaStream_t s);
+int swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int inter, cudaStream_t s);
+int rmsnorm_bwd(const float* x, long long ldx, const float* gamma, const float* dy, long long ldy, float eps, int rows, int D,
+                float* dx, long long lddx, int period, int stride, int offset, cudaStream_t s);
+int rope_bwd_cast(const float* dqkv, void* out, int rows, int T, int H, int hd, int pos0, const float* cos_t,
+                  const float* sin_t, cudaStream_t s);
+int attention_bwd(const void* q, long long ldq, const void* kc, const void* vc, long long ldc, int cache_rows, const void* o,
+                  long long ldo, const void* dout, long long lddo, float* dqkv, int B, int H, int hd, int Tq, int Tk,
+                  float scale, cudaStream_t s);
+int ce_grad(const float* logits, long long ld, int rows, int cols, const int* targets, const float* mean_count, void* dlogits,
+            long long ldd, cudaStream_t s);
+int cast_rows_f32_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols, int period, int stride,
+                       int offset, cudaStream_t s);
+int transpose_bf16(const void* src, long long lds, void* dst, long long ldd, int rows, int cols, cudaStream_t s);
+int colsum_bf16(const void* src, long long lds, int rows, int cols, float* out, cudaStream_t s);
+int adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1, float beta2,
+               float eps, float wd, int step, float gscale, cudaStream_t s);
 }  // namespace cgpt

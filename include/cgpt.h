@@ -201,6 +201,38 @@ int cgpt_gather_rows(const void* table, int64_t ldt, const int32_t* ids, int id_
 int cgpt_gemm_profile_begin(void);
 int cgpt_gemm_profile_end(float* ms_out, int32_t* mnk_out, int capacity, int* count);
 
+/* ---------------------------------------------------------------- fine-tune step: backward + optimiser kernels
+ * MiniGPT4FineTuneAgent.train (agents/minigpt4_finetune_agent.py:149-195): loss.backward() through the frozen Llama to
+ * llama_proj (the only trainable module: base_model.py:162-172,238-240; minigpt4.py:76-78,111-117) and an AdamW step.
+ * The data-gradient GEMMs are cgpt_gemm_bf16 on transposed weight copies; these are the non-GEMM pieces (fp32 math,
+ * fixed summation order).  Host orchestration: certifiedgpt_b200/train.py. */
+/* SwiGLU on a fused gate/up GEMM output gu [rows, 2*inter] bf16, (gate_j, up_j) interleaved: act = silu(gate) * up */
+int cgpt_swiglu_fwd(const void* gu, void* act, int64_t rows, int inter, void* stream);
+int cgpt_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int inter, void* stream);
+/* LlamaRMSNorm backward, accumulated into dx (the residual gradient): dx[map(r)] += d/dx (x r gamma) . dy[r];
+ * row_period > 0: map(r) = (r / period) * stride + offset + r % period (rows the final norm was applied to) */
+int cgpt_rmsnorm_bwd(const float* x, int64_t ldx, const float* gamma, const float* dy, int64_t ldy, float eps, int rows, int D,
+                     float* dx, int64_t lddx, int row_period, int row_stride, int row_offset, void* stream);
+/* transpose of HF's rotary rotation on the q, k parts of dqkv f32 [rows, 3*H*hd] (v copied), cast to bf16 */
+int cgpt_rope_bwd_cast(const float* dqkv, void* out, int rows, int T, int H, int head_dim, int pos0, const float* cos_table,
+                       const float* sin_table, void* stream);
+/* causal attention backward for short sequences (Tq, Tk <= ~128): one CTA per (sample, head); q rotated queries,
+ * keys / values = rows [0, Tk) of the sample's KV cache (shared-prefix rows first); dqkv f32 [B*Tq, 3*H*hd] receives dq and
+ * the dk / dv of the sample's own rows (prefix keys have no gradient consumer) */
+int cgpt_attention_bwd(const void* q, int64_t ldq, const void* kcache, const void* vcache, int64_t ld_cache,
+                       int cache_rows_per_batch, const void* o, int64_t ldo, const void* dout, int64_t lddo, float* dqkv,
+                       int B, int H, int head_dim, int Tq, int Tk, float scale, void* stream);
+/* dlogits bf16 = (softmax(logits) - onehot(target)) / count, zero rows where target < 0; mean_count from cgpt_ce_loss */
+int cgpt_ce_grad(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, const float* mean_count,
+                 void* dlogits, int64_t ldd, void* stream);
+int cgpt_cast_rows_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, int row_period,
+                            int row_stride, int row_offset, void* stream);
+int cgpt_transpose_bf16(const void* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream);
+int cgpt_colsum_bf16(const void* src, int64_t lds, int rows, int cols, float* out, void* stream);
+/* torch.optim.AdamW step on fp32 master weights (decoupled weight decay), refreshing the bf16 copy the GEMMs read */
+int cgpt_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 /* ================================================================= native engine
  * The whole MiniGPT-4 noisy-sample classifier behind one handle: host-side
  * C++ orchestration of the kernels above, CUDA-graph replay per batch size, no Python in the loop.

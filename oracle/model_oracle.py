@@ -240,6 +240,20 @@ def lm_loss(sd, cfg, images, prefix_ids, suffix_ids, answers, prefix="llama_mode
     return loss, tok[:, Lc - 1:Lc - 1 + na]
 
 
+def finetune_grads(sd, cfg, images, prefix_ids, suffix_ids, answers):
+    """loss.backward() of the fine-tune step (agents/minigpt4_finetune_agent.py:165-172) by torch autograd over the
+    restated forward: only llama_proj.weight / .bias require grad (everything else is frozen, base_model.py:162-172,
+    238-240; minigpt4.py:111-117).  Returns (loss, dW, db)."""
+    sd2 = dict(sd)
+    W = sd["llama_proj.weight"].detach().float().clone().requires_grad_(True)
+    b = sd["llama_proj.bias"].detach().float().clone().requires_grad_(True)
+    sd2["llama_proj.weight"], sd2["llama_proj.bias"] = W, b
+    with torch.enable_grad():
+        loss, _ = lm_loss(sd2, cfg, images, prefix_ids, suffix_ids, answers)
+        loss.backward()
+    return loss.detach(), W.grad.detach(), b.grad.detach()
+
+
 def canonical_answer(ids, eos_id=2):
     """Token-level restatement of minigpt_base.py:438-446: decode(skip_special_tokens=True) drops
     <unk>=0,<s>=1,</s>=2; everything after the first EOS is padding."""
