@@ -206,3 +206,27 @@ def test_training_lowers_the_loss_and_updates_the_shared_projection():
     b = tr.forward(images, answers, 0.25, seed=1, step=3).item()
     c = tr.forward(images, answers, 0.25, seed=1, step=4).item()
     assert a == b and a != c
+
+
+def test_finetune_agent_loop_and_lr_schedule():
+    from certifiedgpt_b200.agents import setup_agent
+    from certifiedgpt_b200.agents.minigpt4_finetune_agent import linear_warmup_cosine_lr
+    # the reference scheduler (optims.py:11-73) on its shipped settings: warm-up 1e-6 -> 1e-5 over 53 steps, then cosine
+    kw = dict(max_epoch=4, iters_per_epoch=53, min_lr=1e-6, init_lr=1e-5, warmup_steps=53, warmup_start_lr=1e-6, warmup_max_lr=1e-5)
+    assert linear_warmup_cosine_lr(0, 0, **kw) == pytest.approx(1e-6)
+    assert linear_warmup_cosine_lr(0, 26, **kw) == pytest.approx(1e-6 + 9e-6 * 26 / 53)
+    assert linear_warmup_cosine_lr(1, 0, **kw) == pytest.approx((1e-5 - 1e-6) * 0.5 * (1 + math.cos(math.pi * 53 / 212)) + 1e-6)
+    assert linear_warmup_cosine_lr(3, 52, **kw) < 1.1e-6
+    cfg = ModelConfig.tiny()
+    sd, eng, _ = _trainer(cfg, seed=47)
+    S = cfg.vit.img_size
+    g = torch.Generator().manual_seed(3)
+    train = [{"image": torch.rand(3, S, S, generator=g), "answer_ids": [20 + i % 3, 2]} for i in range(8)]
+    val = [{"image": torch.rand(3, S, S, generator=g), "answer_ids": [20 + i % 3, 2]} for i in range(4)]
+    agent = setup_agent("image_text_finetune", engine=eng, train_set=train, val_set=val, noise_level=0.25, batch_size=4,
+                        max_epoch=6, init_lr=3e-3, min_lr=1e-3, warmup_steps=2, warmup_start_lr=1e-3, warmup_max_lr=3e-3,
+                        weight_decay=0.0, max_answer=4)
+    hist = agent.run()
+    agent.finalize()
+    assert len(hist["train_loss"]) >= 2 and hist["train_loss"][-1] < hist["train_loss"][0]
+    assert agent.best_state is not None and agent.best_val_loss == min(hist["val_loss"])
