@@ -1114,6 +1114,14 @@ int cgpt_comm_destroy(void* comm) {
   return 0;
 }
 
+int cgpt_allreduce_f32(float* values, int64_t n, void* comm, void* stream) {
+  CGPT_REQUIRE(values && comm && n > 0, "cgpt_allreduce_f32: bad argument");
+  CGPT_TRY(load_nccl());
+  // ncclFloat32 = 7, ncclSum = 0
+  CGPT_CHECK_NCCL(g_nccl.AllReduce(values, values, static_cast<size_t>(n), 7, 0, comm, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int cgpt_allreduce_counts(int64_t* counts, int n, void* comm, void* stream) {
   CGPT_REQUIRE(counts && comm && n > 0, "cgpt_allreduce_counts: bad argument");
   CGPT_TRY(load_nccl());

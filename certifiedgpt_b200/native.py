@@ -73,6 +73,7 @@ def _declare(lib):
         "cgpt_comm_init": [vp, i32, i32, C.POINTER(vp)],
         "cgpt_comm_destroy": [vp],
         "cgpt_allreduce_counts": [vp, i32, vp, vp],
+        "cgpt_allreduce_f32": [vp, i64, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -133,6 +134,11 @@ class CountsComm:
         assert counts.dtype == torch.int64 and counts.is_cuda and counts.is_contiguous()
         L.check(lib().cgpt_allreduce_counts(L.ptr(counts), counts.numel(), self.handle, L.stream_ptr()))
         return counts
+
+    def allreduce_f32(self, values):
+        assert values.dtype == torch.float32 and values.is_cuda and values.is_contiguous()
+        L.check(lib().cgpt_allreduce_f32(L.ptr(values), values.numel(), self.handle, L.stream_ptr()))
+        return values
 
     def close(self):
         if self.handle:

@@ -41,6 +41,7 @@ class LlamaProjTrainer:
         self.cfg, self.dev, self.w = engine.cfg, engine.dev, engine.w
         self.lr, self.betas, self.eps, self.wd = float(lr), betas, float(eps), float(weight_decay)
         self.process_group = process_group
+        self._comm = None
         self.step_count = 0
         l, q = self.cfg.llm, self.cfg.qf
         self.P, self.ns = engine.P, len(engine.suffix_ids)
@@ -226,9 +227,12 @@ class LlamaProjTrainer:
             import torch.distributed as dist
             g = None if self.process_group is True else self.process_group
             if dist.get_world_size(g) > 1:
+                if self._comm is None:                                    # libcgpt's own NCCL communicator (NVLink)
+                    from .native import CountsComm
+                    self._comm = CountsComm(self.process_group)
                 for t in self.grads.values():
-                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=g)     # NCCL over NVLink
-                gscale = 1.0 / dist.get_world_size(g)
+                    self._comm.allreduce_f32(t)
+                gscale = 1.0 / dist.get_world_size(g)                     # mean over the ranks
         self.step_count += 1
         lr = self.lr if lr is None else float(lr)
         lib = _lib()

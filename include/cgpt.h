@@ -347,6 +347,9 @@ int cgpt_comm_unique_id(void* id128);
 int cgpt_comm_init(const void* id128, int rank, int world, void** comm);
 int cgpt_comm_destroy(void* comm);
 int cgpt_allreduce_counts(int64_t* counts, int n, void* comm, void* stream);
+/* fp32 sum over the ranks: the llama_proj gradient of the fine-tune step (xm.reduce_gradients,
+ * agents/minigpt4_finetune_agent.py:174), 3.1 M values */
+int cgpt_allreduce_f32(float* values, int64_t n, void* comm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,33 @@ def main():
           and torch.equal(est, single.last_counts_estimation) and int(est.sum()) == n)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    # data-parallel fine-tune step: every rank trains on its own images, the llama_proj gradient is averaged over the
+    # ranks through libcgpt's NCCL communicator -> all ranks hold identical weights afterwards, equal to one process
+    # that averages the per-rank gradients itself
+    if not full:
+        from certifiedgpt_b200.train import LlamaProjTrainer
+        py = MiniGPT4Engine(cfg, sd, prefix, suffix, table, 10, max_new_tokens=4, device=dev, use_graphs=False)
+        tr = LlamaProjTrainer(py, lr=1e-3, weight_decay=0.0, max_batch=2, max_answer=3, process_group=True)
+        gi = torch.Generator().manual_seed(77)
+        all_images = torch.rand(world * 2, 3, S, S, generator=gi)
+        all_answers = torch.randint(3, V, (world * 2, 3), generator=gi)
+        tr.forward(all_images[rank * 2:rank * 2 + 2].to(dev), all_answers[rank * 2:rank * 2 + 2], 0.0)
+        gW, gb = tr.backward()
+        local_gW = gW.clone()
+        tr.optimizer_step()
+        gathered = [torch.empty_like(local_gW) for _ in range(world)]
+        dist.all_gather(gathered, local_gW)
+        mean_gW = torch.stack(gathered).mean(0)
+        same_w = [torch.empty_like(tr.Wp) for _ in range(world)]
+        dist.all_gather(same_w, tr.Wp)
+        train_ok = (all(torch.equal(same_w[0], t) for t in same_w)
+                    and torch.allclose(tr.grads["W"] / world, mean_gW, rtol=1e-5, atol=1e-7))
+        ok = ok and train_ok
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"data-parallel fine-tune step over {world} ranks: weights identical on all ranks and gradient = mean of the "
+                  f"per-rank gradients: {'TRAIN_DIST_OK' if train_ok else 'TRAIN_DIST_MISMATCH'}", flush=True)
     if rank == 0:
         print(f"engine={Engine.__name__} world={world} sharded={res} single={res1} counts_est={est.tolist()} "
               f"{'DIST_OK' if flag.item() == 1 else 'DIST_MISMATCH'}", flush=True)
