@@ -92,31 +92,46 @@ __global__ void rope_bwd_cast_kernel(const float* __restrict__ dqkv, __nv_bfloat
 // included), Tk - Tq = number of keys before the first query; o: forward output; dout: gradient wrt o.
 // dqkv (f32 [B*Tq, 3*H*hd]) receives dq, and dk / dv for the keys that belong to this sample's own rows
 // (key j >= Tk - Tq <-> row j - (Tk - Tq)); gradients of the shared prefix keys are dropped (no parameter behind them).
+// Q, K, V, dO sit in shared memory as bf16 with rows padded by 16 bytes (consecutive rows start 4 banks apart, so a
+// warp reading 32 different rows at one column offset needs the minimum 4 wavefronts); every inner loop consumes
+// 8 bf16 per 16-byte load.
+__device__ __forceinline__ float dot8(const uint4 a, const uint4 b) {
+  return bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
+         bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+}
+__device__ __forceinline__ void axpy8(float* acc, float w, const uint4 v) {
+  acc[0] = fmaf(w, bf16_lo(v.x), acc[0]); acc[1] = fmaf(w, bf16_hi(v.x), acc[1]);
+  acc[2] = fmaf(w, bf16_lo(v.y), acc[2]); acc[3] = fmaf(w, bf16_hi(v.y), acc[3]);
+  acc[4] = fmaf(w, bf16_lo(v.z), acc[4]); acc[5] = fmaf(w, bf16_hi(v.z), acc[5]);
+  acc[6] = fmaf(w, bf16_lo(v.w), acc[6]); acc[7] = fmaf(w, bf16_hi(v.w), acc[7]);
+}
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, long long ldq,
                                                        const __nv_bfloat16* __restrict__ kc,
                                                        const __nv_bfloat16* __restrict__ vc, long long ldc, int cache_rows,
                                                        const __nv_bfloat16* __restrict__ o, long long ldo,
                                                        const __nv_bfloat16* __restrict__ dout, long long lddo,
                                                        float* __restrict__ dqkv, int H, int hd, int Tq, int Tk, float scale) {
-  extern __shared__ uint8_t smem_raw[];
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [Tq, hd]
-  __nv_bfloat16* sK = sQ + Tq * hd;                                        // [Tk, hd]
-  __nv_bfloat16* sV = sK + Tk * hd;                                        // [Tk, hd]
-  __nv_bfloat16* sD = sV + Tk * hd;                                        // [Tq, hd]  dO
-  float* sP = reinterpret_cast<float*>(sD + Tq * hd);                      // [Tq, Tk]  P, then dS
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int hp = hd + 8;                                                   // padded row, elements
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [Tq, hp]
+  __nv_bfloat16* sK = sQ + Tq * hp;                                        // [Tk, hp]
+  __nv_bfloat16* sV = sK + Tk * hp;                                        // [Tk, hp]
+  __nv_bfloat16* sD = sV + Tk * hp;                                        // [Tq, hp]  dO
+  float* sP = reinterpret_cast<float*>(sD + Tq * hp);                      // [Tq, Tk]  P, then dS
   float* sDelta = sP + Tq * Tk;                                            // [Tq]
   const int h = blockIdx.x % H, b = blockIdx.x / H;
-  const int off = Tk - Tq, D = H * hd;
+  const int off = Tk - Tq, D = H * hd, nc = hd >> 3;                       // nc: 16-byte chunks per head row
   const long long qrow0 = static_cast<long long>(b) * Tq, krow0 = static_cast<long long>(b) * cache_rows;
-  for (int i = threadIdx.x; i < Tq * hd; i += 256) {
-    const int r = i / hd, c = i - r * hd;
-    sQ[i] = q[(qrow0 + r) * ldq + h * hd + c];
-    sD[i] = dout[(qrow0 + r) * lddo + h * hd + c];
+  auto row16 = [&](const __nv_bfloat16* base, int r, int c) { return *reinterpret_cast<const uint4*>(base + r * hp + c * 8); };
+  for (int e = threadIdx.x; e < Tq * nc; e += 256) {
+    const int r = e / nc, c = e - r * nc;
+    *reinterpret_cast<uint4*>(sQ + r * hp + c * 8) = *reinterpret_cast<const uint4*>(q + (qrow0 + r) * ldq + h * hd + c * 8);
+    *reinterpret_cast<uint4*>(sD + r * hp + c * 8) = *reinterpret_cast<const uint4*>(dout + (qrow0 + r) * lddo + h * hd + c * 8);
   }
-  for (int i = threadIdx.x; i < Tk * hd; i += 256) {
-    const int r = i / hd, c = i - r * hd;
-    sK[i] = kc[(krow0 + r) * ldc + h * hd + c];
-    sV[i] = vc[(krow0 + r) * ldc + h * hd + c];
+  for (int e = threadIdx.x; e < Tk * nc; e += 256) {
+    const int r = e / nc, c = e - r * nc;
+    *reinterpret_cast<uint4*>(sK + r * hp + c * 8) = *reinterpret_cast<const uint4*>(kc + (krow0 + r) * ldc + h * hd + c * 8);
+    *reinterpret_cast<uint4*>(sV + r * hp + c * 8) = *reinterpret_cast<const uint4*>(vc + (krow0 + r) * ldc + h * hd + c * 8);
   }
   __syncthreads();
   // S = scale * Q K^T with the causal mask (query i sees keys <= i + off)
@@ -125,7 +140,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const __nv_bfloat16* __re
     float acc = -INFINITY;
     if (j <= i + off) {
       acc = 0.f;
-      for (int c = 0; c < hd; ++c) acc = fmaf(bf(sQ[i * hd + c]), bf(sK[j * hd + c]), acc);
+      for (int c = 0; c < nc; ++c) acc += dot8(row16(sQ, i, c), row16(sK, j, c));
       acc *= scale;
     }
     sP[e] = acc;
@@ -147,18 +162,20 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const __nv_bfloat16* __re
     const float inv = 1.f / sum;
     for (int j = lane; j < Tk; j += 32) sP[i * Tk + j] *= inv;
     float dl = 0.f;
-    for (int c = lane; c < hd; c += 32) dl = fmaf(bf(sD[i * hd + c]), bf(o[(qrow0 + i) * ldo + h * hd + c]), dl);
+    for (int c = lane; c < hd; c += 32) dl = fmaf(bf(sD[i * hp + c]), bf(o[(qrow0 + i) * ldo + h * hd + c]), dl);
     dl = warp_sum(dl);
     if (lane == 0) sDelta[i] = dl;
   }
   __syncthreads();
-  // dV[j] = sum_i P_ij dO_i  (own keys only)
-  for (int e = threadIdx.x; e < Tq * hd; e += 256) {
-    const int jr = e / hd, c = e - jr * hd;          // own row jr <-> key j = jr + off
+  // dV[j, 8 cols] = sum_i P_ij dO_i  (own keys only; P is zero above the diagonal, so i starts at the key's own row)
+  for (int e = threadIdx.x; e < Tq * nc; e += 256) {
+    const int jr = e / nc, c = e - jr * nc;            // own row jr <-> key j = jr + off
     const int j = jr + off;
-    float acc = 0.f;
-    for (int i = jr; i < Tq; ++i) acc = fmaf(sP[i * Tk + j], bf(sD[i * hd + c]), acc);   // causal: i >= jr
-    dqkv[(qrow0 + jr) * 3 * D + 2 * D + h * hd + c] = acc;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = jr; i < Tq; ++i) axpy8(acc, sP[i * Tk + j], row16(sD, i, c));
+    float* dst = dqkv + (qrow0 + jr) * 3 * D + 2 * D + h * hd + c * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
   __syncthreads();
   // dS_ij = P_ij (dO_i . V_j - delta_i), in place
@@ -167,22 +184,26 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const __nv_bfloat16* __re
     float v = 0.f;
     if (j <= i + off) {
       float dp = 0.f;
-      for (int c = 0; c < hd; ++c) dp = fmaf(bf(sD[i * hd + c]), bf(sV[j * hd + c]), dp);
+      for (int c = 0; c < nc; ++c) dp += dot8(row16(sD, i, c), row16(sV, j, c));
       v = sP[e] * (dp - sDelta[i]);
     }
     sP[e] = v;
   }
   __syncthreads();
   // dQ_i = scale * sum_j dS_ij K_j ;  dK_j = scale * sum_i dS_ij Q_i (own keys only)
-  for (int e = threadIdx.x; e < Tq * hd; e += 256) {
-    const int i = e / hd, c = e - i * hd;
-    float aq = 0.f;
-    for (int j = 0; j <= i + off; ++j) aq = fmaf(sP[i * Tk + j], bf(sK[j * hd + c]), aq);
-    dqkv[(qrow0 + i) * 3 * D + h * hd + c] = aq * scale;
-    const int j = i + off;                           // own key of row i
-    float ak = 0.f;
-    for (int ii = i; ii < Tq; ++ii) ak = fmaf(sP[ii * Tk + j], bf(sQ[ii * hd + c]), ak);
-    dqkv[(qrow0 + i) * 3 * D + D + h * hd + c] = ak * scale;
+  for (int e = threadIdx.x; e < Tq * nc; e += 256) {
+    const int i = e / nc, c = e - i * nc;
+    float aq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j <= i + off; ++j) axpy8(aq, sP[i * Tk + j], row16(sK, j, c));
+    float* dq = dqkv + (qrow0 + i) * 3 * D + h * hd + c * 8;
+    *reinterpret_cast<float4*>(dq) = make_float4(aq[0] * scale, aq[1] * scale, aq[2] * scale, aq[3] * scale);
+    *reinterpret_cast<float4*>(dq + 4) = make_float4(aq[4] * scale, aq[5] * scale, aq[6] * scale, aq[7] * scale);
+    const int j = i + off;                             // own key of row i
+    float ak[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int ii = i; ii < Tq; ++ii) axpy8(ak, sP[ii * Tk + j], row16(sQ, ii, c));
+    float* dk = dqkv + (qrow0 + i) * 3 * D + D + h * hd + c * 8;
+    *reinterpret_cast<float4*>(dk) = make_float4(ak[0] * scale, ak[1] * scale, ak[2] * scale, ak[3] * scale);
+    *reinterpret_cast<float4*>(dk + 4) = make_float4(ak[4] * scale, ak[5] * scale, ak[6] * scale, ak[7] * scale);
   }
 }
 
@@ -310,7 +331,9 @@ int attention_bwd(const void* q, long long ldq, const void* kc, const void* vc, 
                   float scale, cudaStream_t s) {
   CGPT_REQUIRE(q && kc && vc && o && dout && dqkv, "attention_bwd: null argument");
   CGPT_REQUIRE(B > 0 && H > 0 && hd > 0 && Tq > 0 && Tk >= Tq && Tk <= cache_rows, "attention_bwd: bad sizes Tq=%d Tk=%d", Tq, Tk);
-  const size_t smem = static_cast<size_t>(2 * Tq + 2 * Tk) * hd * 2 + static_cast<size_t>(Tq) * Tk * 4 + Tq * 4;
+  CGPT_REQUIRE(hd % 8 == 0 && ldq % 8 == 0 && ldc % 8 == 0 && lddo % 8 == 0 && (H * hd) % 4 == 0,
+               "attention_bwd: head_dim and leading dimensions must be multiples of 8");
+  const size_t smem = static_cast<size_t>(2 * Tq + 2 * Tk) * (hd + 8) * 2 + static_cast<size_t>(Tq) * Tk * 4 + Tq * 4;
   CGPT_REQUIRE(smem <= 227 * 1024, "attention_bwd: Tq=%d Tk=%d hd=%d needs %zu bytes of shared memory", Tq, Tk, hd, smem);
   static size_t configured = 0;
   if (smem > configured) {
