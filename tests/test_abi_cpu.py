@@ -53,27 +53,31 @@ def test_answer_hash_canonicalisation_host():
     assert L.answer_hash([5]) != L.answer_hash([5, 5])
 
 
-def test_native_engine_structs_match_the_header():
-    """ctypes mirrors of cgpt_model_config / cgpt_noise_spec: one field per header field, same order."""
-    from certifiedgpt_b200 import native as N
+def _struct_fields(struct):
+    """field names of a C struct in include/cgpt.h, in declaration order"""
     src = open(os.path.join(ROOT, "include", "cgpt.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), src, flags=re.S).group(1)
+    out = []
+    for decl in body.split(";"):
+        for declarator in decl.split(","):
+            names = re.findall(r"[A-Za-z_]\w*", re.sub(r"\[.*?\]", "", declarator))
+            if names:
+                out.append(names[-1])
+    return out
 
-    def fields(struct):
-        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), src, flags=re.S).group(1)
-        out = []
-        for decl in body.split(";"):
-            decl = decl.strip()
-            if not decl:
-                continue
-            names = decl.split(None, 1)[1] if not decl.startswith("const") else decl.split("*")[1]
-            out += [re.sub(r"\[.*?\]", "", n).strip().lstrip("*") for n in names.split(",")]
-        return out
 
-    assert fields("cgpt_model_config") == [f[0] for f in N.ModelConfigC._fields_]
-    assert fields("cgpt_noise_spec") == [f[0] for f in N.NoiseSpecC._fields_]
+def test_ctypes_mirrors_match_the_header_structs():
+    """ctypes mirrors of every struct that crosses the ABI: one field per header field, same order."""
+    from certifiedgpt_b200 import _lib as L
+    from certifiedgpt_b200 import native as N
+    for struct, mirror in [("cgpt_model_config", N.ModelConfigC), ("cgpt_noise_spec", N.NoiseSpecC),
+                           ("cgpt_gemm_epilogue", L.GemmEpilogue), ("cgpt_gemm_rope", L.GemmRope),
+                           ("cgpt_attn_args", L.AttnArgs)]:
+        assert _struct_fields(struct) == [f[0] for f in mirror._fields_], struct
     assert ctypes.sizeof(N.ModelConfigC) == 4 * len(N.ModelConfigC._fields_)
     assert ctypes.sizeof(N.NoiseSpecC) == 56
+    assert ctypes.sizeof(L.GemmRope) == 64 and ctypes.sizeof(L.GemmEpilogue) == 104
 
 
 def test_native_engine_refuses_to_start_without_a_gpu():
