@@ -654,12 +654,14 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   int bn = (force_bn & 0xfff);
   if (bn == 0) bn = ctas == 2 ? (N > 176 ? 256 : (N > 128 ? 176 : 128)) : pick_bn(N);
   {
-    // 16 m-tiles per band.  Measured (ncu, profiles/r01_gemm_band_traffic.txt): shrinking the band for the
-    // long-K residual GEMMs (6 tiles at K = 11008 so that the A band is 34 MB instead of 90 MB) does not lower
-    // their DRAM reads (14.9 vs 13.6 GB for Llama down) and costs nothing in time either way, so the band stays
-    // fixed; CGPT_GEMM_GROUP_M overrides it for experiments.
+    // Band height.  A weight that fits L2 several times over (ViT / Q-Former linears, <= 24 MB) stays resident
+    // whatever the order, so a LOW band (4 m-tiles) is best: the n-tiles that share an A tile then run close
+    // together and A is read from HBM once (ViT fc2: 10.6 -> 7.2 GB of DRAM reads, 4.00 -> 3.63 ms per launch, ncu).
+    // The big Llama weights (90-180 MB) must instead be amortised over a high band of 16 m-tiles.
+    // Sweep: profiles/r01_gemm_band_traffic.txt; CGPT_GEMM_GROUP_M overrides.
     static const int forced = getenv("CGPT_GEMM_GROUP_M") ? atoi(getenv("CGPT_GEMM_GROUP_M")) : 0;
-    p.group_m = forced > 0 ? forced : GROUP_M_MAX;
+    const long long w_bytes = static_cast<long long>(N) * K * 2;
+    p.group_m = forced > 0 ? forced : (w_bytes <= (24LL << 20) ? 4 : GROUP_M_MAX);
   }
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, A, M, K, lda, BM)) return rc;
