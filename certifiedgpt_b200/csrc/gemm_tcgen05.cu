@@ -683,8 +683,13 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   p.remap_stride = e->remap_stride; p.remap_offset = e->remap_offset;
   p.red_inplace = (p.resid != nullptr && p.resid == p.out && p.out_f32 && p.resid_f32 && p.ldr == p.ldo &&
                    p.act == CGPT_ACT_NONE && p.row_add == nullptr && !getenv("CGPT_GEMM_NO_RED")) ? 1 : 0;
-  // 2 = warp-transposed, sector-coalesced reductions (CGPT_GEMM_RED_DIRECT=1 keeps the row-per-thread form for A/B)
-  if (p.red_inplace && p.ldo % 4 == 0 && !getenv("CGPT_GEMM_RED_DIRECT")) p.red_inplace = 2;
+  // 2 = warp-transposed, sector-coalesced reductions, for the SHORT-K GEMMs whose epilogue outlasts their MMAs (ViT
+  // proj, K = 1408: 775 -> 1102 TFLOP/s).  Long-K GEMMs hide the direct form behind the MMAs, and inside the
+  // power-capped step the extra shared-memory round trip cost them 1-4 % (A/B, gpurun_out/ab_red*.log), so they keep
+  // it.  CGPT_GEMM_RED_DIRECT=1 / CGPT_GEMM_RED_COALESCED=1 force one form for experiments.
+  if (p.red_inplace && p.ldo % 4 == 0 && !getenv("CGPT_GEMM_RED_DIRECT") &&
+      (K <= 2048 || getenv("CGPT_GEMM_RED_COALESCED")))
+    p.red_inplace = 2;
   p.dbg = reinterpret_cast<long long*>(getenv("CGPT_GEMM_DBG") ? strtoull(getenv("CGPT_GEMM_DBG"), nullptr, 0) : 0ull);
   const cgpt_gemm_rope* rp = e->rope;
   if (rp != nullptr) {
