@@ -95,3 +95,35 @@ def test_native_engine_refuses_to_start_without_a_gpu():
     assert rc != 0 and not hd.value and len(h.cgpt_last_error()) > 0
     bad = N.config_struct(ModelConfig.tiny(), 3, 4, 0, 1, 6, True, True)    # max_new_tokens = 0
     assert h.cgpt_create(ctypes.byref(bad), ctypes.byref(hd)) == -1
+
+
+def test_header_is_plain_c99_and_struct_sizes_match_ctypes(tmp_path):
+    """include/cgpt.h must be consumable by a C FFI (cgo / JNI / ctypes generators): compile it as C99 with gcc and
+    compare sizeof() of every struct that crosses the ABI with the ctypes mirrors."""
+    import shutil
+    import subprocess
+    from certifiedgpt_b200 import _lib as L
+    from certifiedgpt_b200 import native as N
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "cgpt.h"\nint main(void) { printf("%zu %zu %zu %zu %zu\\n", '
+                   "sizeof(cgpt_model_config), sizeof(cgpt_noise_spec), sizeof(cgpt_gemm_epilogue), sizeof(cgpt_gemm_rope), "
+                   "sizeof(cgpt_attn_args)); return 0; }\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(t) for t in (N.ModelConfigC, N.NoiseSpecC, L.GemmEpilogue, L.GemmRope, L.AttnArgs)]
+    assert got == want
+
+
+def test_lr_schedule_matches_the_reference_scheduler():
+    """LinearWarmupCosineLRScheduler.step (graphs/models/minigpt4/common/optims.py:11-73) on the shipped settings."""
+    import math
+    from certifiedgpt_b200.agents.minigpt4_finetune_agent import linear_warmup_cosine_lr
+    kw = dict(max_epoch=4, iters_per_epoch=53, min_lr=1e-6, init_lr=1e-5, warmup_steps=53, warmup_start_lr=1e-6, warmup_max_lr=1e-5)
+    assert linear_warmup_cosine_lr(0, 0, **kw) == pytest.approx(1e-6)
+    assert linear_warmup_cosine_lr(0, 26, **kw) == pytest.approx(1e-6 + 9e-6 * 26 / 53)
+    assert linear_warmup_cosine_lr(1, 0, **kw) == pytest.approx((1e-5 - 1e-6) * 0.5 * (1 + math.cos(math.pi * 53 / 212)) + 1e-6)
+    assert linear_warmup_cosine_lr(3, 52, **kw) < 1.1e-6
