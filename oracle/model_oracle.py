@@ -17,6 +17,10 @@ follows (paths under /root/reference/graphs/models/minigpt4/models/ unless noted
   generate_ids       minigpt_base.py:374-427 (greedy, min_length=1, EOS=2, pad after EOS) as
                      HF GenerationMixin greedy search executes it
   answer_label       minigpt_base.py:438-446 + agents/minigpt4_eval_agent.py:102 at token level
+  lm_loss            minigpt_base.py:323-362 (training / validation forward) + modeling_llama.py:101-123 (shifted CE);
+                     pinned against transformers.LlamaForCausalLM(inputs_embeds, labels).loss
+  finetune_grads     loss.backward() of agents/minigpt4_finetune_agent.py:165-172 by torch autograd over lm_loss
+                     (only llama_proj requires grad: base_model.py:162-172,238-240; minigpt4.py:111-117)
 
 Pinning: tests/golden/ref_*.pt hold outputs of the reference's OWN eva_vit.py / Qformer.py
 modules (imported by file path in the build container, script tests/golden/make_ref_fixtures.py);
