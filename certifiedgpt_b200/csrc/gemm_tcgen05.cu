@@ -544,7 +544,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
       if constexpr (ROPE) {
         // BN = 256: this warp's half of the tile is one 128-wide head
-        epilogue_rope_head(t_row + half * 128, epi, m, row_ok, n_base + half * 128);
+        if (n_base + half * 128 < N) epilogue_rope_head(t_row + half * 128, epi, m, row_ok, n_base + half * 128);
       } else if (epi.red_inplace == 2) {
         epilogue_chunks_red(t_row, epi, bias_s, red_stage + warp * (32 * 20), m_blk * BM + quarter * 32, M, n_base, N,
                             half == 0 ? 0 : NCH0, half == 0 ? NCH0 : NCH);

@@ -28,7 +28,9 @@ def _close(y, r, tol=1.6e-2):
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (128, 256, 128, 256), (128, 176, 128, 176),
                                       (300, 1408, 592, 0), (771, 4224, 1408, 0), (1, 768, 768, 0),
-                                      (20000, 1408, 1408, 0), (130, 1408, 6144, 0), (79, 32000, 4096, 0)])
+                                      (20000, 1408, 1408, 0), (130, 1408, 6144, 0), (79, 32000, 4096, 0),
+                                      # masked last n-tile of the CTA-pair kernel: 32 / 80 / 208 / 16 valid columns
+                                      (700, 1312, 256, 0), (700, 1360, 256, 0), (700, 1488, 256, 0), (700, 1040, 256, 0)])
 def test_gemm_plain(lib, M, N, K, bn):
     torch.manual_seed(M + N + K)
     a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
