@@ -717,6 +717,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   // masked tail; 1-CTA tiles prefer an exact divisor of N
   int bn = (force_bn & 0xfff);
   if (bn == 0) bn = ctas == 2 ? (N > 176 ? 256 : (N > 128 ? 176 : 128)) : pick_bn(N);
+  if (rp != nullptr) bn = 256;   // the fused rotary epilogue needs one 128-wide head per epilogue warp
   {
     // Band height.  A weight that fits L2 several times over (ViT / Q-Former linears, <= 24 MB) stays resident
     // whatever the order, so a LOW band (4 m-tiles) is best: the n-tiles that share an A tile then run close

@@ -85,7 +85,8 @@ def test_gemm_rejects_bad_shapes(lib):
 
 
 @pytest.mark.parametrize("B,T,heads,pos0,row0,rows", [(3, 72, 4, 7, 7, 83), (40, 1, 4, 80, 80, 83), (5, 7, 32, 0, 0, 7),
-                                                      (130, 5, 2, 3, 9, 20)])
+                                                      (130, 5, 2, 3, 9, 20),
+                                                      (10, 8, 3, 2, 2, 12), (40, 8, 3, 2, 2, 12)])   # odd head count: half-empty last tile
 def test_fused_rope_kv_append_epilogue_matches_separate_pass(lib, B, T, heads, pos0, row0, rows):
     """QKV GEMM with the fused rotary + KV-cache-append epilogue vs plain GEMM + cgpt_rope_split and vs an fp32
     torch restatement of HF's apply_rotary_pos_emb (rotate_half).  The fused path rotates the fp32 accumulators
