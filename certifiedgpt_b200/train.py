@@ -18,7 +18,6 @@ Host orchestration only; every number is produced by libcgpt.so:
             cgpt_rope_bwd_cast -> llama_proj weight gradient = one GEMM over transposed operands, bias gradient = column sum
   step      (all-reduce of the 3.1 M gradient values over the ranks) -> cgpt_adamw_step on fp32 master weights
 """
-import ctypes as C
 import math
 
 import torch
