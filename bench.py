@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--img-size", type=int, default=224)
     ap.add_argument("--n0", type=int, default=N0)
     ap.add_argument("--n", type=int, default=N)
-    ap.add_argument("--cpu-samples", type=int, default=2, help="bounded CPU-baseline sample (noisy samples)")
+    ap.add_argument("--cpu-samples", type=int, default=8,
+                    help="bounded CPU-baseline sample (noisy samples; ~10 s of host work at ~1 sample/s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="tiny model (debug only; not a bench number)")
     ap.add_argument("--engine", default="native", choices=["native", "python"],
@@ -163,7 +164,7 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = 1 if args.steps + args.warmup > 6 else 2
+    per_step = 2 if args.steps + args.warmup > 6 else 4   # bounded: ~1 sample/s on 16 cores
     run, cores = cpu_reference_runner(cfg, args.max_new_tokens)
     for _ in range(args.warmup):
         run(per_step)

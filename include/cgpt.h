@@ -306,7 +306,8 @@ int cgpt_llm_prefill_decode(cgpt_handle h, const void* queries, int B, int32_t* 
  * ViT -> Q-Former -> llama_proj; the sequence [prefix | image | suffix | answer] runs through the frozen Llama and the
  * answer tokens are scored.  answer_ids: device int32 [B, na], -100 = padding (ignored); na <= max_new_tokens.
  * out_token_loss: device f32 [B*na]; out_mean_count: device f32 [2] = {mean loss over scored tokens, their count}.
- * Forward only: the backward pass for the llama_proj gradient is not part of this library yet. */
+ * Forward only: the backward pass to the llama_proj gradient is orchestrated by certifiedgpt_b200/train.py over the
+ * backward / optimiser kernels declared above (cgpt_attention_bwd, cgpt_rmsnorm_bwd, cgpt_ce_grad, cgpt_adamw_step). */
 int cgpt_lm_loss(cgpt_handle h, const void* patches, int B, const int32_t* answer_ids, int na, float* out_token_loss,
                  float* out_mean_count, void* stream);
 /* one batch of the hot loop: labels[b] = class of f(x + sigma * eps_{first_sample + b}), b < B.
