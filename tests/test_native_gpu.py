@@ -271,3 +271,74 @@ def test_ce_loss_kernel_matches_torch():
     ref = torch.nn.functional.cross_entropy(logits.double(), tg, ignore_index=-100, reduction="none")
     assert (tok.cpu().double() - ref).abs().max().item() < 1e-4
     assert abs(mc[0].item() - ref.sum().item() / 35) < 1e-4 and mc[1].item() == 35
+
+
+def _raw_sample_noise(nat, x, num, batch_size, sigma, rank, world, split=None, base=0, seed=3):
+    """cgpt_sample_noise for one (rank, world) slice without a communicator: this rank's own counts."""
+    import ctypes as C
+    from certifiedgpt_b200 import _lib as L
+    nat.reserve(max(1, min(batch_size, num)))
+    spec = nat._spec(sigma, seed, 0, L.SPACE_NORMALIZED, L.NOISE_GAUSSIAN, L.BLIP_MEAN, L.BLIP_STD)
+    nvec = 1 if split is None else 2
+    counts = torch.full((nvec, nat.num_classes), -7, dtype=torch.int64, device="cuda")   # the call must zero them
+    invalid = torch.empty(1, dtype=torch.int32, device="cuda")
+    L.check(nat._lib.cgpt_sample_noise(nat._h, C.c_void_p(x.data_ptr()), C.byref(spec), base, num, batch_size,
+                                       -1 if split is None else split, rank, world, None, L.ptr(counts),
+                                       L.ptr(invalid), L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert int(invalid.item()) == 0
+    return counts.cpu().numpy()
+
+
+def test_rank_slices_sum_to_the_single_rank_counts_incl_empty_slices():
+    """SURVEY 8(e) on one GPU: the union of the per-rank slices of [base, base+num) is the 1-rank run, for world
+    sizes that do not divide num, for more ranks than draws (empty slices) and with the selection/estimation split."""
+    cfg = ModelConfig.tiny()
+    n_classes = 6
+    sd, py, nat, _ = _setup(cfg, seed=9, max_new=2, n_classes=n_classes)
+    S = cfg.vit.img_size
+    x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(11)).cuda()
+    for num, split, base in [(45, None, 0), (45, 10, 0), (5, 2, 7), (1, None, 0)]:
+        whole = _raw_sample_noise(nat, x, num, 16, 0.5, 0, 1, split=split, base=base)
+        assert whole.sum() == num
+        if split is not None:
+            assert whole[0].sum() == split and whole[1].sum() == num - split
+        for world in (2, 3, 8):
+            parts = [_raw_sample_noise(nat, x, num, 16, 0.5, r, world, split=split, base=base) for r in range(world)]
+            assert np.array_equal(sum(parts), whole), (num, split, base, world)
+            sizes = [int(p.sum()) for p in parts]
+            assert max(sizes) - min(sizes) <= 1                        # balanced contiguous slices
+    # the same draws through a different batch size and through the Python twin's Smooth loop
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    whole = _raw_sample_noise(nat, x, 45, 16, 0.5, 0, 1)
+    assert np.array_equal(_raw_sample_noise(nat, x, 45, 1, 0.5, 0, 1), whole)
+    assert np.array_equal(_raw_sample_noise(nat, x, 45, 4096, 0.5, 0, 1), whole)
+    assert np.array_equal(Smooth(py, n_classes, 0.5, seed=3)._sample_noise(x, 45, 7), whole[0])
+
+
+def test_empty_and_single_draw_calls():
+    """num = 0 runs no batch and returns zero counts (smoothing.py:91: range(ceil(0 / batch_size)) is empty);
+    one-draw certify / predict abstain (alpha ** 1 < 0.5; binomial test of 1 vs 0 gives p = 1)."""
+    from certifiedgpt_b200 import _lib as L
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    cfg = ModelConfig.tiny()
+    n_classes = 6
+    sd, py, nat, _ = _setup(cfg, seed=9, max_new=2, n_classes=n_classes)
+    S = cfg.vit.img_size
+    x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(11)).cuda()
+    assert _raw_sample_noise(nat, x, 0, 16, 0.5, 0, 1).sum() == 0
+    assert _raw_sample_noise(nat, x, 0, 16, 0.5, 1, 2, split=0).sum() == 0
+    for eng in (nat, py):
+        sm = Smooth(eng, n_classes, 0.5, seed=3)
+        z = sm._sample_noise(x, 0, 16)
+        assert z.shape == (n_classes,) and z.sum() == 0
+        assert sm.certify(x, 1, 1, 0.001, 1000) == (Smooth.ABSTAIN, 0.0)
+        assert sm.predict(x, 1, 0.001, 1000) == Smooth.ABSTAIN
+    # bad arguments come back as errors, not as crashes
+    import ctypes as C
+    spec = nat._spec(0.5, 0, 0, L.SPACE_NORMALIZED, L.NOISE_GAUSSIAN, L.BLIP_MEAN, L.BLIP_STD)
+    counts = torch.zeros(2, n_classes, dtype=torch.int64, device="cuda")
+    for num, bs, split, rank, world in [(-1, 8, -1, 0, 1), (8, 0, -1, 0, 1), (8, 8, 9, 0, 1), (8, 8, -1, 2, 2)]:
+        rc = nat._lib.cgpt_sample_noise(nat._h, C.c_void_p(x.data_ptr()), C.byref(spec), 0, num, bs, split, rank, world,
+                                        None, L.ptr(counts), None, L.stream_ptr())
+        assert rc != 0 and nat._lib.cgpt_last_error()

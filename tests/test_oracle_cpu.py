@@ -98,3 +98,22 @@ def test_smooth_oracle_end_to_end_cpu():
     assert np.array_equal(c, c2)
     label = s.predict(x, 40, 0.001, 16)
     assert label in (-1, int(c.argmax()))
+
+
+def test_smooth_oracle_edge_cases_of_the_reference_loop():
+    """smoothing.py:91-99: num = 0 runs no batch; a batch size above num runs ONE short batch; one draw can never
+    certify (alpha ** 1 < 0.5) nor pass the binomial test (p = 1)."""
+    model = _Toy()
+    x = torch.rand(3, 8, 8, generator=torch.Generator().manual_seed(2))
+    seen = []
+    s = so.SmoothOracle(model, 5, 0.25, noise_fn=lambda d, c, b: (seen.append(c), torch.zeros_like(b))[1])
+    z = s._sample_noise(x, 0, 16)
+    assert z.tolist() == [0] * 5 and seen == []
+    c = s._sample_noise(x, 5, 1000)
+    assert seen == [5] and c.sum() == 5 and c.max() == 5           # zero noise: every draw votes the same class
+    seen.clear()
+    s._sample_noise(x, 37, 16)
+    assert seen == [16, 16, 5]
+    assert s.certify(x, 1, 1, 0.001, 8) == (-1, 0.0)
+    assert s.predict(x, 1, 0.001, 8) == -1
+    assert so.lower_confidence_bound(1, 1, 0.001) == pytest.approx(0.001, rel=1e-12)   # alpha ** (1 / n)

@@ -94,3 +94,33 @@ def test_helpers_match_reference_semantics():
     assert s._lower_confidence_bound(990, 1000, 0.001) == pytest.approx(0.9760361871553114, rel=1e-9)
     assert s._lower_confidence_bound(0, 1000, 0.001) == 0.0
     assert Smooth.ABSTAIN == -1
+
+
+def test_edge_cases_follow_the_reference_loop():
+    """Empty and ragged draws as smoothing.py:91-99 handles them: num = 0 runs no batch (all-zero counts), a batch
+    size larger than num runs one short batch, batch size 1 walks sample by sample; a one-draw certify abstains."""
+    oracle, ours, x, cur, model = _pair(n_total=64)
+    xc = x.cuda()
+    ours._cursor = 0
+    zero = ours._sample_noise(xc, 0, 32)
+    assert zero.shape == (6,) and zero.sum() == 0
+    assert np.array_equal(oracle._sample_noise(x, 0, 32), zero)
+    cur["base"] = 0
+    ref = oracle._sample_noise(x, 37, 1000)
+    for bs in (1000, 37, 36, 5, 1):
+        ours._cursor = 0
+        assert np.array_equal(ours._sample_noise(xc, 37, bs), ref), bs
+    # n0 = n = 1: pABar = alpha ** 1 < 0.5 -> ABSTAIN, radius exactly 0.0 (smoothing.py:53-54)
+    assert ours.certify(xc, 1, 1, 0.001, 1000) == (-1, 0.0)
+    cur["base"] = 0
+    assert oracle.certify(x, 1, 1, 0.001, 1000) == (-1, 0.0)
+    # predict on one draw: binomial test of 1 vs 0 has p = 1 > alpha -> ABSTAIN (smoothing.py:76-77)
+    assert ours.predict(xc, 1, 0.001, 8) == -1
+
+
+def test_rejects_host_tensor_on_the_generic_path():
+    from certifiedgpt_b200 import _lib as L
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    s = Smooth(Toy(4, (3, 16, 16)).cuda(), 4, 0.5)
+    with pytest.raises(L.CgptError):
+        s._sample_noise(torch.rand(3, 16, 16), 8, 8)      # no CPU path exists
