@@ -658,6 +658,31 @@ static int pick_bn(int N) {
   return N >= 256 ? 256 : (N > 128 ? 176 : 128);
 }
 
+// Skinny problems (one or two m-tiles: the decode steps, and every GEMM of a small per-rank batch) are bound by how
+// many SMs stream the weight, not by the tensor pipe: with 256-wide tiles an N = 4096 projection keeps 16 CTA pairs
+// busy and N = 22016 runs 74 + 12 tiles.  Pick the N tile that minimises waves x (tile width + fixed cost), and leave
+// 256 unless the model predicts >= 15 % (measured at M = 138: down 71.7 -> 53.2 us with 128-wide tiles,
+// scripts/gemm_wave_probe.py).  The tile width does not change any element's K summation order, so results stay
+// bit-identical across batch sizes.  CGPT_GEMM_NO_SKINNY=1 disables.
+static int pick_bn_skinny(int M, int N, int ctas, int bn_default, int workers) {
+  static const bool off = getenv("CGPT_GEMM_NO_SKINNY") != nullptr;
+  const int m_tiles = (M + BM * ctas - 1) / (BM * ctas);
+  if (off || m_tiles > 2 || N < 512 || workers <= 0) return bn_default;
+  auto cost = [&](int bn) {
+    const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
+    return ((tiles + workers - 1) / workers) * (bn + 64);
+  };
+  const long long cost_default = cost(bn_default);
+  long long best_cost = cost_default;
+  int best = bn_default;
+  const int cand[3] = {256, 176, 128};
+  for (int i = 0; i < 3; ++i) {
+    const long long c = cost(cand[i]);
+    if (c < best_cost) { best_cost = c; best = cand[i]; }
+  }
+  return best_cost * 100 <= cost_default * 85 ? best : bn_default;
+}
+
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
               const cgpt_gemm_epilogue* e, int force_bn, cudaStream_t stream) {
   CGPT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
@@ -717,6 +742,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   // masked tail; 1-CTA tiles prefer an exact divisor of N
   int bn = (force_bn & 0xfff);
   if (bn == 0) bn = ctas == 2 ? (N > 176 ? 256 : (N > 128 ? 176 : 128)) : pick_bn(N);
+  if ((force_bn & 0xfff) == 0 && rp == nullptr && e->max_ctas == 0) bn = pick_bn_skinny(M, N, ctas, bn, g_num_sms / ctas);
   if (rp != nullptr) bn = 256;   // the fused rotary epilogue needs one 128-wide head per epilogue warp
   {
     // Band height.  A weight that fits L2 several times over (ViT / Q-Former linears, <= 24 MB) stays resident
