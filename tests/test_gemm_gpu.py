@@ -131,3 +131,43 @@ def test_fused_rope_kv_append_epilogue_matches_separate_pass(lib, B, T, heads, p
     assert (kc1[:, keep] == 7.0).all() and (vc1[:, keep] == -3.0).all()
     # v is a plain copy in both paths: bit-identical
     assert torch.equal(vc1[:, row0:row0 + T], vc2[:, row0:row0 + T])
+
+
+@pytest.mark.parametrize("M", [1, 100, 138, 275])
+@pytest.mark.parametrize("N,K,kind", [(4096, 1024, "resid"), (4096, 4096, "resid"), (22016, 512, "swiglu"), (32000, 256, "f32"),
+                                      (1408, 768, "bias"), (4224, 256, "plain")])
+def test_skinny_tile_choice_is_bit_identical_to_256_wide_tiles(lib, M, N, K, kind):
+    """For one or two m-tiles gemm_bf16 picks the N tile by wave cost (pick_bn_skinny).  The tile width never changes an
+    element's K summation order: the automatic choice, forced 256- and forced 128-wide tiles must agree bit for bit
+    (this is what keeps labels independent of the batch size), and all match the fp32 reference."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    pair = 0x2000 if M > 128 else 0x1000
+    outs = []
+    for flag in (0, pair | 256, pair | 128):
+        if kind == "resid":
+            r = torch.arange(M * N, device="cuda", dtype=torch.float32).view(M, N) * 1e-6
+            lib.gemm(a, w, resid=r, out=r, force_bn=flag)
+            outs.append(r)
+        elif kind == "swiglu":
+            outs.append(lib.gemm(a, w, act=lib.ACT_SWIGLU, force_bn=flag))
+        elif kind == "f32":
+            outs.append(lib.gemm(a, w, out_dtype=torch.float32, force_bn=flag))
+        elif kind == "bias":
+            outs.append(lib.gemm(a, w, bias=torch.linspace(-1, 1, N, device="cuda"), force_bn=flag))
+        else:
+            outs.append(lib.gemm(a, w, force_bn=flag))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    if kind == "resid":
+        ref = _ref(a, w) + torch.arange(M * N, device="cuda", dtype=torch.float32).view(M, N) * 1e-6
+        assert torch.allclose(outs[0], ref, atol=2e-3, rtol=1e-4)
+    elif kind == "swiglu":
+        _close(outs[0], _ref(a, w, act=2), tol=2e-2)
+    elif kind == "f32":
+        assert torch.allclose(outs[0], _ref(a, w), atol=2e-3, rtol=1e-4)
+    elif kind == "bias":
+        _close(outs[0], _ref(a, w, torch.linspace(-1, 1, N, device="cuda")))
+    else:
+        _close(outs[0], _ref(a, w))
