@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcgpt.so")
+# CGPT_LIB=<path>: load another build of the same ABI (A/B runs of two kernel versions inside one gpurun call)
+LIB_PATH = os.environ.get("CGPT_LIB") or os.path.join(_HERE, "lib", "libcgpt.so")
 
 DT_BF16, DT_F32 = 0, 1
 ACT_NONE, ACT_GELU, ACT_SWIGLU, ACT_QUICKGELU = 0, 1, 2, 3

@@ -51,7 +51,9 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, PrefillAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: a round trip through uintptr_t would
+  // lose the address space and turn every shared-memory access below into a generic LD.E / ST.E
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // [P0 | P1 | load stage 0 .. NL-1 | barriers].  The UMMA A operand always spans 128 rows: for q_pad < 128 it
   // reads past a Q / P sub-tile into the bytes that follow (finite or not, those rows are never stored), so
   // the P tiles sit in FRONT of the load ring and nothing is read beyond the allocation.

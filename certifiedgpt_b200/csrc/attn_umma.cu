@@ -61,7 +61,9 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_v1,
                  UmmaAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: a round trip through uintptr_t would
+  // lose the address space and turn every shared-memory access below into a generic LD.E / ST.E
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                       // n_qtiles x [sub0 | sub1]
   uint8_t* sK = smem + p.q_bytes;           // [sub0 | sub1], sub stride nk_pad*128; later P of q-tile 0
   uint8_t* sV = sK + p.k_region;            // [sub0 | sub1]
