@@ -127,3 +127,14 @@ def test_lr_schedule_matches_the_reference_scheduler():
     assert linear_warmup_cosine_lr(0, 26, **kw) == pytest.approx(1e-6 + 9e-6 * 26 / 53)
     assert linear_warmup_cosine_lr(1, 0, **kw) == pytest.approx((1e-5 - 1e-6) * 0.5 * (1 + math.cos(math.pi * 53 / 212)) + 1e-6)
     assert linear_warmup_cosine_lr(3, 52, **kw) < 1.1e-6
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps each C symbol of include/cgpt.h to the reference lines it replaces."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "cgpt.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    syms = sorted(set(re.findall(r"\b(cgpt_[a-z0-9_]+)\s*\(", header)))
+    assert len(syms) >= 50
+    assert [s for s in syms if s not in doc] == []
