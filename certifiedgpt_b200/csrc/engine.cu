@@ -198,7 +198,6 @@ struct Epi {
 inline int gemm(const void* A, long long lda, const void* W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
   return gemm_bf16(A, lda, W, K, M, N, K, &epi.e, 0, s);
 }
-inline const __nv_bfloat16* bf(const void* p) { return static_cast<const __nv_bfloat16*>(p); }
 inline __nv_bfloat16* bf(void* p) { return static_cast<__nv_bfloat16*>(p); }
 
 int attn(const void* q, long long ldq, int q_rows, const void* k, const void* v, long long ldkv, int kv_rows,
