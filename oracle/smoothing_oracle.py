@@ -11,9 +11,16 @@ replaced by their exact SciPy equivalents:
      (statsmodels' method="beta" lower limit is exactly this Clopper-Pearson quantile)
 
 Parity status: the reference ships no tests, golden vectors or fixtures for this path
- -> "parity unpinned by reference tests"; it is pinned instead by the
-known-answer table of SURVEY.md 8(c) (tests/golden/smoothing_kat.json, generated with the
-SciPy calls above) and by Cohen et al.'s published algorithm which the file copies.
+(SURVEY.md F3), so nothing of the reference's own test suite pins it.  It is pinned by
+(a) OUTPUTS OF THE REFERENCE FILE ITSELF: tests/golden/make_ref_smooth_fixtures.py executes
+smoothing.py unmodified in the build container (behind shims for the two library calls above and
+for the hard-coded noise device) on seeded classifiers, images and draws, and
+tests/golden/ref_smooth.json holds its count vectors, certify / predict results and
+_lower_confidence_bound values - this module reproduces them exactly
+(tests/test_oracle_cpu.py::test_oracle_equals_the_reference_smooth_run), and so does the CUDA path
+(tests/test_smooth_gpu.py::test_cuda_smooth_equals_the_reference_smooth_run);
+(b) the known-answer table of SURVEY.md 8(c) (tests/golden/smoothing_kat.json, generated with the
+SciPy calls above).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module.

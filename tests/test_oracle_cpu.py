@@ -117,3 +117,36 @@ def test_smooth_oracle_edge_cases_of_the_reference_loop():
     assert s.certify(x, 1, 1, 0.001, 8) == (-1, 0.0)
     assert s.predict(x, 1, 0.001, 8) == -1
     assert so.lower_confidence_bound(1, 1, 0.001) == pytest.approx(0.001, rel=1e-12)   # alpha ** (1 / n)
+
+
+from ref_smooth_util import REF_SMOOTH, case_id, ref_smooth_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("case", REF_SMOOTH["cases"], ids=case_id)
+def test_oracle_equals_the_reference_smooth_run(case):
+    """The oracle restatement against outputs of the reference's OWN smoothing.py (executed unmodified in the build
+    container on the same seeded classifier, image and draws): count vectors, certify and predict results."""
+    model, x, eps = ref_smooth_inputs(case)
+    cur = {"base": 0}
+    s = so.SmoothOracle(model, case["classes"], case["sigma"],
+                        noise_fn=lambda d, c, b: eps[cur["base"] + d: cur["base"] + d + c])
+    n0, n, bs, alpha = case["n0"], case["n"], case["batch_size"], case["alpha"]
+    sel = s._sample_noise(x, n0, bs)
+    cur["base"] = n0
+    est = s._sample_noise(x, n, bs)
+    assert sel.tolist() == case["counts_selection"] and est.tolist() == case["counts_estimation"]
+    label, radius = so.certify_tail(sel, est, n, alpha, case["sigma"])
+    assert label == case["certify"][0] and radius == pytest.approx(case["certify"][1], rel=1e-12, abs=0)
+    cur["base"] = 0
+    assert s.predict(x, n, alpha, bs) == case["predict"]
+    cur["base"] = 0
+    assert s._sample_noise(x, n, bs).tolist() == case["predict_counts"]
+
+
+def test_oracle_helpers_equal_the_reference_run():
+    for row in REF_SMOOTH["lower_confidence_bound"]:
+        assert so.lower_confidence_bound(row["NA"], row["N"], row["alpha"]) == pytest.approx(row["value"], rel=1e-13, abs=0)
+    ca = REF_SMOOTH["count_arr"]
+    s = so.SmoothOracle(None, ca["length"], 0.25)
+    assert s._count_arr(np.array(ca["arr"]), ca["length"]).tolist() == ca["counts"]
+    assert so.SmoothOracle.ABSTAIN == REF_SMOOTH["ABSTAIN"] == -1

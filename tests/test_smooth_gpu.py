@@ -124,3 +124,27 @@ def test_rejects_host_tensor_on_the_generic_path():
     s = Smooth(Toy(4, (3, 16, 16)).cuda(), 4, 0.5)
     with pytest.raises(L.CgptError):
         s._sample_noise(torch.rand(3, 16, 16), 8, 8)      # no CPU path exists
+
+
+from ref_smooth_util import REF_SMOOTH, case_id, ref_smooth_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("case", REF_SMOOTH["cases"], ids=case_id)
+def test_cuda_smooth_equals_the_reference_smooth_run(case):
+    """The CUDA path against outputs of the reference's OWN smoothing.py (tests/golden/make_ref_smooth_fixtures.py ran it
+    unmodified on the same seeded classifier, image and draws): count vectors, (label, radius) and predict, exactly."""
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    model, x, eps = ref_smooth_inputs(case)
+    n0, n, bs, alpha = case["n0"], case["n"], case["batch_size"], case["alpha"]
+    ours = Smooth(model.cuda(), case["classes"], case["sigma"])
+    ours.inject_noise(eps.cuda())
+    label, radius = ours.certify(x.cuda(), n0, n, alpha, bs)
+    assert ours.last_counts_selection.cpu().tolist() == case["counts_selection"]
+    assert ours.last_counts_estimation.cpu().tolist() == case["counts_estimation"]
+    assert label == case["certify"][0] and radius == pytest.approx(case["certify"][1], rel=1e-9, abs=0)
+    # the reference's two separate _sample_noise calls (no fused selection pass) give the same result
+    seq = Smooth(model.cuda(), case["classes"], case["sigma"], fuse_selection=False)
+    seq.inject_noise(eps.cuda())
+    assert seq.certify(x.cuda(), n0, n, alpha, bs) == (label, radius)
+    assert ours.predict(x.cuda(), n, alpha, bs) == case["predict"]
+    assert ours.last_counts.cpu().tolist() == case["predict_counts"]
