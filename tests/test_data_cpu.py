@@ -11,30 +11,14 @@ import torch
 from certifiedgpt_b200.data import vqav2 as V
 
 
+import ref_data_util as U  # noqa: E402
+
+REF_DATA = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_data.json")))
+
+
 @pytest.fixture()
 def fake_vqav2(tmp_path):
-    from PIL import Image
-    rng = np.random.default_rng(0)
-    img_dir = tmp_path / "train2014"
-    img_dir.mkdir()
-    ids = [42, 9, 123456]
-    for i, iid in enumerate(ids):
-        arr = rng.integers(0, 256, size=(60 + 10 * i, 80, 3), dtype=np.uint8)
-        Image.fromarray(arr).save(img_dir / f"COCO_train2014_{iid:012d}.jpg", quality=95)
-    questions = {"questions": [{"question_id": 1000 + i, "image_id": iid, "question": q}
-                               for i, (iid, q) in enumerate(zip(ids, ["What color is the car?", "Is it raining!?", "How many (dogs)?"]))]}
-    questions["questions"].append({"question_id": 7, "image_id": 9, "question": "unused"})
-    ann = {"annotations": [
-        {"question_id": 1000, "image_id": 42, "answers": [{"answer": "red", "answer_confidence": "yes"}] * 7
-         + [{"answer": "dark red", "answer_confidence": "maybe"}] * 2 + [{"answer": "blue", "answer_confidence": "no"}]},
-        {"question_id": 1001, "image_id": 9, "answers": [{"answer": "No.", "answer_confidence": "yes"}] * 10},
-        {"question_id": 1002, "image_id": 123456, "answers": [{"answer": "2", "answer_confidence": "maybe"}] * 3
-         + [{"answer": "", "answer_confidence": "yes"}]},
-    ]}
-    qp, ap = tmp_path / "q.json", tmp_path / "a.json"
-    qp.write_text(json.dumps(questions))
-    ap.write_text(json.dumps(ann))
-    return str(qp), str(ap), str(img_dir)
+    return U.build(str(tmp_path))
 
 
 def test_image_processor_equals_torchvision_pipeline(fake_vqav2):
@@ -88,3 +72,35 @@ def test_prompt_split_and_agent_items(fake_vqav2):
     assert [it["label"] for it in items] == [0, 1, 2]                    # "No." normalises to "no"
     ft = V.finetune_items(ds, enc)
     assert ft[1]["answer_ids"] == enc("no</s>") and ft[1]["image"].shape == (3, 56, 56)
+
+
+@pytest.mark.parametrize("size", [56, 224])
+def test_items_equal_the_reference_loader_run(fake_vqav2, size):
+    """Every item of the reference's OWN VQAv2Dataset + Blip2ImageTrainProcessor + BlipCaptionProcessor (executed
+    unmodified by tests/golden/make_ref_data_fixtures.py on the same files, global `random` seeded): question ids,
+    instruction strings, sampled answers and the processed image."""
+    qp, ap, img_dir = fake_vqav2
+    rec = REF_DATA["image_sizes"][str(size)]
+    for seed in (1, 2):
+        ds = V.VQAv2Dataset([qp], [ap], img_dir, split="train", vis_processor=V.ImageProcessor(size), seed=seed)
+        assert len(ds) == rec["len"]
+        for want in [r for r in rec["items"] if r["seed"] == seed]:
+            got = ds[want["index"]]
+            assert got["question_id"] == want["question_id"]
+            assert got["instruction_input"] == want["instruction_input"]
+            assert got["answer"] == want["answer"]
+            assert list(got["image"].shape) == want["shape"]
+            dg = U.image_digest(got["image"])
+            assert dg["sum"] == pytest.approx(want["image"]["sum"], rel=1e-6, abs=1e-3)
+            assert dg["sumsq"] == pytest.approx(want["image"]["sumsq"], rel=1e-6)
+            assert np.allclose(dg["pooled"], want["image"]["pooled"], atol=1e-5)
+
+
+def test_text_processor_and_answer_sampling_equal_the_reference_run(fake_vqav2):
+    for row in REF_DATA["pre_caption"]:
+        assert V.pre_caption(row["in"]) == row["out"]
+    for row in REF_DATA["pre_caption_max3"]:
+        assert V.pre_caption(row["in"], max_words=3) == row["out"]
+    qp, ap, img_dir = fake_vqav2
+    ds = V.VQAv2Dataset([qp], [ap], img_dir, split="train", vis_processor=V.ImageProcessor(56), seed=3)
+    assert [ds.get_data(0)["answer"] for _ in range(400)] == REF_DATA["answer_draws_seed3"]
