@@ -127,6 +127,12 @@ def test_lr_schedule_matches_the_reference_scheduler():
     assert linear_warmup_cosine_lr(0, 26, **kw) == pytest.approx(1e-6 + 9e-6 * 26 / 53)
     assert linear_warmup_cosine_lr(1, 0, **kw) == pytest.approx((1e-5 - 1e-6) * 0.5 * (1 + math.cos(math.pi * 53 / 212)) + 1e-6)
     assert linear_warmup_cosine_lr(3, 52, **kw) < 1.1e-6
+    # every (epoch, step) of three settings against a run of the reference's own scheduler (tests/golden/make_ref_lr_fixture.py)
+    import json
+    for rec in json.load(open(os.path.join(ROOT, "tests", "golden", "ref_lr.json"))):
+        kw = rec["settings"]
+        got = [linear_warmup_cosine_lr(e, s, **kw) for e in range(kw["max_epoch"]) for s in range(kw["iters_per_epoch"])]
+        assert got == pytest.approx(rec["lr"], rel=1e-15, abs=0)
 
 
 def test_integration_doc_names_every_entry_point():
