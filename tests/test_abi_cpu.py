@@ -144,3 +144,26 @@ def test_integration_doc_names_every_entry_point():
     syms = sorted(set(re.findall(r"\b(cgpt_[a-z0-9_]+)\s*\(", header)))
     assert len(syms) >= 50
     assert [s for s in syms if s not in doc] == []
+
+
+def test_plain_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """tests/c/abi_client.c: a C99 program linked against libcgpt.so alone (what a cgo / JNI binding links): host helpers
+    work, argument errors come back as status + message, and on this CPU-only host cgpt_create refuses to start."""
+    import shutil
+    import subprocess
+    import torch
+    from certifiedgpt_b200 import _lib as L
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(L.LIB_PATH)
+    exe = tmp_path / "abi_client"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_client.c"), "-o", str(exe), "-L", libdir, "-lcgpt",
+                           f"-Wl,-rpath,{libdir}"])
+    args = [str(exe)] + (["--gpu"] if torch.cuda.is_available() else [])
+    r = subprocess.run(args, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "abi_client ok" in r.stdout
+    # the library's only dynamic dependencies are the C/C++ runtimes (CUDA runtime linked statically, NCCL dlopen'ed)
+    deps = subprocess.check_output(["ldd", L.LIB_PATH], text=True)
+    assert "libtorch" not in deps and "libpython" not in deps and "libnccl" not in deps
