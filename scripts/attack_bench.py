@@ -4,7 +4,6 @@ Random-init weights, synthetic images.  python scripts/attack_bench.py [--no-vic
 import json
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

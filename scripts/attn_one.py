@@ -1,5 +1,5 @@
 """One attention shape, a few launches (ncu target). usage: attn_one.py vit|llm B"""
-import sys, os, math
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from certifiedgpt_b200 import _lib as L

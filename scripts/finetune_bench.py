@@ -9,7 +9,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import bench
-from certifiedgpt_b200 import _lib as L
 from certifiedgpt_b200.config import ModelConfig
 from certifiedgpt_b200.engine import MiniGPT4Engine
 from certifiedgpt_b200.train import LlamaProjTrainer

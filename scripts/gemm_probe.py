@@ -1,6 +1,6 @@
 """GPU probe for the tcgen05 GEMM: correctness across shapes/epilogues, then throughput.
 Run under gpurun; prints one line per case and never stops at the first failure."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from certifiedgpt_b200 import _lib as L

@@ -1,5 +1,5 @@
 """Kernel-time breakdown of one full-size noisy batch (CUPTI via torch.profiler; no ncu replay)."""
-import os, sys, json
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity

@@ -1,7 +1,5 @@
 """GPU parity: attention kernels (tcgen05 one-shot, mma.sync flash, single-token decode) vs an fp32
 torch reference of softmax(scale * Q K^T [+ causal]) V on the same bf16 inputs."""
-import math
-
 import pytest
 import torch
 

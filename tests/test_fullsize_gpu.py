@@ -1,6 +1,5 @@
 """GPU parity at BASELINE.json's full encoder size (EVA ViT-g/14 39L + Q-Former 12L) and
 size-independent properties of the whole path at full MiniGPT-4 shape."""
-import numpy as np
 import pytest
 import torch
 

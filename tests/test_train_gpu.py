@@ -4,7 +4,6 @@
 * the whole step (forward with kept activations, backward through the frozen decoder, llama_proj gradient) against
   the CPU oracle's autograd over the restated reference forward (oracle.finetune_grads), bf16 tolerance;
 * training on a fixed batch lowers the loss, and the generate path sees the updated llama_proj."""
-import ctypes as C
 import math
 
 import pytest
