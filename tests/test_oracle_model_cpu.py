@@ -134,3 +134,41 @@ def test_lm_loss_matches_hf_causal_lm_loss():
     assert abs(loss.item() - ref.item()) < 1e-5
     assert tok.shape == (3, 3) and tok[1, 2].item() == 0.0 and (tok[answers >= 0] > 0).all()
     assert abs(tok.sum().item() / 8 - loss.item()) < 1e-5
+
+
+def _ref_generate_cases():
+    return torch.load(os.path.join(GOLD, "ref_generate.pt"))["cases"]
+
+
+@pytest.mark.parametrize("rec", _ref_generate_cases(), ids=lambda r: r["case"]["name"])
+def test_prompt_assembly_and_generate_equal_the_reference_generate_run(rec):
+    """The oracle's glue (build_prompt_embeds / generate_ids / canonical_answer) and the product's split_prompt against a
+    run of the reference's OWN MiniGPTBase.generate + get_context_emb + embed_tokens (tests/golden/
+    make_ref_generate_fixtures.py): the embeddings handed to llama_model.generate, its arguments, the generated ids
+    (min_length, EOS, pad) and the post-processed answer strings."""
+    from certifiedgpt_b200.data import vqav2 as V
+    from ref_generate_util import encode
+    case = rec["case"]
+    cfg = ModelConfig.tiny()
+    cfg.llm = LlmConfig(hidden=64, layers=2, heads=4, inter=128, vocab=96)
+    sd = random_state_dict(cfg, seed=case["seed"])
+    if case["eos_boost"]:
+        sd["llama_model.lm_head.weight"][cfg.llm.eos_id] *= case["eos_boost"]
+    kw = rec["generate_kwargs"]
+    assert kw["do_sample"] is False and kw["num_beams"] == 1 and kw["min_length"] == 1
+    assert kw["max_new_tokens"] == case["max_new_tokens"]
+    ref_ids, ref_emb, ref_mask = rec["outputs"], rec["inputs_embeds"], rec["attention_mask"]
+    enc = lambda s: encode(s, cfg.llm.vocab)
+    for b, text in enumerate(case["texts"]):
+        prefix, suffix = V.split_prompt(text, enc, prompt_template="{}")     # the agents' prompt is already wrapped
+        assert prefix[0] == 1 and 1 not in suffix                           # BOS on the first segment only (:79-82)
+        emb = mo.build_prompt_embeds(sd, cfg, rec["img_embeds"][b:b + 1], prefix, suffix)
+        S = emb.shape[1]
+        assert int(ref_mask[b].sum()) == S and bool((ref_mask[b, -S:] == 1).all())      # left padding (:405-412)
+        assert torch.equal(emb[0], ref_emb[b, -S:])
+        assert bool((ref_emb[b, :-S] == 0).all()) if S < ref_emb.shape[1] else True
+        ids = mo.generate_ids(sd, cfg, emb, max_new_tokens=case["max_new_tokens"])[0][0]
+        n = ref_ids.shape[1]
+        assert ids[:n].tolist() == ref_ids[b].tolist()
+        assert (ids[n:] == cfg.llm.pad_id).all()
+        assert " ".join(f"t{t}" for t in mo.canonical_answer(ids.tolist(), cfg.llm.eos_id)) == rec["answers"][b]
