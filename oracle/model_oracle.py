@@ -24,7 +24,9 @@ follows (paths under /root/reference/graphs/models/minigpt4/models/ unless noted
 
 Pinning: tests/golden/ref_*.pt hold outputs of the reference's OWN eva_vit.py / Qformer.py
 modules (imported by file path in the build container, script tests/golden/make_ref_fixtures.py);
-tests/test_oracle_model_cpu.py checks this restatement against them.  tests/golden/ref_generate.pt holds a run of the
+tests/test_oracle_model_cpu.py checks this restatement against them; tests/golden/ref_encode_img.pt is a run of the
+reference's OWN MiniGPT4.encode_img (minigpt4.py:121-149) over those modules (the whole tower and its wiring).
+tests/golden/ref_generate.pt holds a run of the
 reference's OWN MiniGPTBase.generate / get_context_emb / embed_tokens (minigpt_base.py, executed unmodified by
 tests/golden/make_ref_generate_fixtures.py on a stub `self` with this image's transformers Llama): the embeddings handed to
 llama_model.generate, its arguments, the generated ids and the post-processed answers; build_prompt_embeds, generate_ids and

@@ -172,3 +172,21 @@ def test_prompt_assembly_and_generate_equal_the_reference_generate_run(rec):
         assert ids[:n].tolist() == ref_ids[b].tolist()
         assert (ids[n:] == cfg.llm.pad_id).all()
         assert " ".join(f"t{t}" for t in mo.canonical_answer(ids.tolist(), cfg.llm.eos_id)) == rec["answers"][b]
+
+
+@pytest.mark.parametrize("name,cfg", [("tiny", ModelConfig.tiny()),
+                                      # full ViT-g / Q-Former / llama_proj widths; the Llama tail is drawn after llama_proj
+                                      # (weights.random_state_dict), so shrinking it leaves the tower's weights unchanged
+                                      ("wide", ModelConfig(vit=VitConfig(img_size=56, depth=1), qf=QFormerConfig(layers=2),
+                                                           llm=LlmConfig(layers=1, inter=128, vocab=96)))])
+def test_encode_img_equals_the_reference_encode_img_run(name, cfg):
+    """The whole image tower (A6-A10) against a run of the reference's OWN MiniGPT4.encode_img over its own
+    VisionTransformer and Q-Former layers (tests/golden/make_ref_encode_img_fixture.py) on the same seeded weights."""
+    ref = torch.load(os.path.join(GOLD, "ref_encode_img.pt"))[name]
+    sd = random_state_dict(cfg, seed=ref["seed"])
+    with torch.no_grad():
+        out = mo.encode_img(sd, cfg, ref["images"])
+    assert out.shape == (3, cfg.qf.n_query, cfg.llm.hidden)
+    assert torch.allclose(out[..., ::ref["stride"]], ref["inputs_llama"], atol=3e-5, rtol=1e-5)
+    assert float(out.double().sum()) == pytest.approx(ref["sum"], abs=2e-2)
+    assert float(out.double().abs().sum()) == pytest.approx(ref["abs_sum"], rel=1e-5)
