@@ -144,3 +144,22 @@ def test_noisy_labels_per_sample_match_oracle_where_margin_safe():
     # Philox path: same engine, no injected noise, label histogram sums to B
     lab2 = eng.noisy_labels(x.cuda(), B, 0.5, seed=3)
     assert lab2.numel() == B and int(lab2.min()) >= 0 and int(lab2.max()) < 6
+
+
+@pytest.mark.parametrize("name,cfg", [("tiny", ModelConfig.tiny()),
+                                      ("wide", ModelConfig(vit=VitConfig(img_size=56, depth=1), qf=QFormerConfig(layers=2),
+                                                           llm=LlmConfig(layers=1, inter=128, vocab=96)))])
+def test_image_tower_matches_the_reference_encode_img_run(name, cfg):
+    """CUDA image tower (noise-free batch of distinct images) against the run of the reference's OWN MiniGPT4.encode_img
+    over its own ViT / Q-Former modules (tests/golden/ref_encode_img.pt, fp32 weights): bf16 tolerance."""
+    import os
+    from certifiedgpt_b200.engine import MiniGPT4Engine
+    ref = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ref_encode_img.pt"))[name]
+    sd = random_state_dict(cfg, seed=ref["seed"])
+    eng = MiniGPT4Engine(cfg, sd, (1, 5, 6), (7, 8, 9), [((3,), 0)], 2, max_new_tokens=1)
+    got = {}
+    eng.forward_images(ref["images"].cuda(), collect=got)
+    torch.cuda.synchronize()
+    tower = got["llm_in"][:, :cfg.qf.n_query].float().cpu()
+    assert tower.shape == (3, cfg.qf.n_query, cfg.llm.hidden)
+    assert _rel(tower[..., ::ref["stride"]], ref["inputs_llama"]) < REL
