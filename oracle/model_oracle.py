@@ -30,7 +30,8 @@ tests/golden/ref_generate.pt holds a run of the
 reference's OWN MiniGPTBase.generate / get_context_emb / embed_tokens (minigpt_base.py, executed unmodified by
 tests/golden/make_ref_generate_fixtures.py on a stub `self` with this image's transformers Llama): the embeddings handed to
 llama_model.generate, its arguments, the generated ids and the post-processed answers; build_prompt_embeds, generate_ids and
-canonical_answer reproduce them exactly.
+canonical_answer reproduce them exactly.  tests/golden/ref_forward.pt is the same for the training forward
+(MiniGPTBase.forward / preparing_embedding / prompt_wrap / concat_emb_input_output): lm_loss reproduces its inputs, labels and loss.
 """
 import math
 

@@ -44,6 +44,7 @@ def load_reference():
     core, xm = types.ModuleType("torch_xla.core"), types.ModuleType("torch_xla.core.xla_model")
     amp.autocast = contextlib.nullcontext
     xm.master_print = lambda *a, **k: None
+    xm.xla_device = lambda: torch.device("cpu")
     xla.amp, xla.core, core.xla_model = amp, core, xm
     sys.modules.update({"torch_xla": xla, "torch_xla.amp": amp, "torch_xla.core": core, "torch_xla.core.xla_model": xm})
     common, creg = types.ModuleType("common"), types.ModuleType("common.registry")

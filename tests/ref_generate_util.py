@@ -21,24 +21,49 @@ def encode(text, vocab):
     return [3 + (ord(c) % (vocab - 3)) for c in text]
 
 
+SPECIAL = {"<unk>": 0, "<s>": 1, "</s>": 2}
+
+
+def encode_special(text, vocab):
+    """encode() with the literal strings <s>, </s>, <unk> mapped to their ids, as LlamaTokenizer does"""
+    import re
+    ids = []
+    for piece in re.split(r"(<s>|</s>|<unk>)", text):
+        if piece in SPECIAL:
+            ids.append(SPECIAL[piece])
+        elif piece:
+            ids.extend(encode(piece, vocab))
+    return ids
+
+
 class _Enc:
-    def __init__(self, ids):
-        self.input_ids = torch.tensor([ids], dtype=torch.long)
+    def __init__(self, rows, pad_id):
+        n = max(len(r) for r in rows)
+        self.input_ids = torch.tensor([r + [pad_id] * (n - len(r)) for r in rows], dtype=torch.long)
+        self.attention_mask = torch.tensor([[1] * len(r) + [0] * (n - len(r)) for r in rows], dtype=torch.long)
 
     def to(self, device):
         return self
 
 
 class CharTokenizer:
-    """The part of LlamaTokenizer the reference's generate path touches (minigpt_base.py:79-82,441)."""
+    """The part of LlamaTokenizer the reference's generate and training-forward paths touch (minigpt_base.py:79-82,
+    120-131,299-306,441): single strings or right-padded batches, BOS only with add_special_tokens, the literal
+    "</s>" of end_sym mapped to the EOS id."""
     padding_side = "right"
+    pad_token_id, bos_token_id, eos_token_id = 0, 1, 2
+    bos_token = "<s>"
 
     def __init__(self, vocab):
         self.vocab = vocab
 
-    def __call__(self, text, return_tensors="pt", add_special_tokens=True, **kw):
-        ids = encode(text, self.vocab)
-        return _Enc(([1] if add_special_tokens else []) + ids)
+    def __call__(self, text, return_tensors="pt", add_special_tokens=True, padding=False, truncation=False,
+                 max_length=None, **kw):
+        rows = []
+        for t in ([text] if isinstance(text, str) else list(text)):
+            ids = ([1] if add_special_tokens else []) + encode_special(t, self.vocab)
+            rows.append(ids[:max_length] if truncation and max_length else ids)
+        return _Enc(rows, self.pad_token_id)
 
     def decode(self, ids, skip_special_tokens=False):
         names = {0: "<unk>", 1: "<s>", 2: "</s>"}

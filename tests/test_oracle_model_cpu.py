@@ -190,3 +190,36 @@ def test_encode_img_equals_the_reference_encode_img_run(name, cfg):
     assert torch.allclose(out[..., ::ref["stride"]], ref["inputs_llama"], atol=3e-5, rtol=1e-5)
     assert float(out.double().sum()) == pytest.approx(ref["sum"], abs=2e-2)
     assert float(out.double().abs().sum()) == pytest.approx(ref["abs_sum"], rel=1e-5)
+
+
+@pytest.mark.parametrize("rec", torch.load(os.path.join(GOLD, "ref_forward.pt"))["cases"], ids=lambda r: r["case"]["name"])
+def test_training_forward_equals_the_reference_forward_run(rec):
+    """oracle.lm_loss (and the product's split_prompt / answer tokenisation) against a run of the reference's OWN
+    MiniGPTBase.forward -> preparing_embedding -> prompt_wrap -> concat_emb_input_output (tests/golden/
+    make_ref_forward_fixture.py): the embeddings and labels handed to the Llama and the mean cross-entropy."""
+    from certifiedgpt_b200.data import vqav2 as V
+    from ref_generate_util import encode_special
+    case = rec["case"]
+    cfg = ModelConfig.tiny()
+    cfg.llm = LlmConfig(hidden=64, layers=2, heads=4, inter=128, vocab=96)
+    sd = random_state_dict(cfg, seed=case["seed"])
+    enc = lambda s: encode_special(s, cfg.llm.vocab)
+    prefix, suffix = V.split_prompt(case["instruction"], enc)               # wraps with "[INST] {} [/INST]"
+    rows = [enc(a + V.END_SYM) for a in case["answers"]]
+    na = max(len(r) for r in rows)
+    answers = torch.tensor([r + [-100] * (na - len(r)) for r in rows])
+    assert all(r[-1] == cfg.llm.eos_id for r in rows)
+    with torch.no_grad():
+        loss, tok = mo.lm_loss(sd, cfg, rec["images"], prefix, suffix, answers)
+        cond = mo.build_prompt_embeds(sd, cfg, mo.encode_img(sd, cfg, rec["images"]), prefix, suffix)
+    assert loss.item() == pytest.approx(rec["loss"], abs=2e-5)
+    Lc = cond.shape[1]
+    labels = torch.full((len(rows), Lc + na), -100, dtype=torch.long)
+    labels[:, Lc:] = answers
+    assert torch.equal(labels, rec["labels"])                                # only the answer positions are scored
+    assert torch.equal(rec["attention_mask"][:, :Lc].long(), torch.ones(len(rows), Lc, dtype=torch.long))
+    assert torch.equal(rec["attention_mask"][:, Lc:].long(), (answers >= 0).long())
+    assert torch.allclose(cond, rec["inputs_embeds"][:, :Lc], atol=1e-6)     # [bos + prompt | image | rest of the prompt]
+    emb = sd["llama_model.model.embed_tokens.weight"]
+    assert torch.equal(emb[answers.clamp_min(0).masked_fill(answers < 0, cfg.llm.pad_id)], rec["inputs_embeds"][:, Lc:])
+    assert tok.shape == answers.shape and bool((tok[answers < 0] == 0).all())
