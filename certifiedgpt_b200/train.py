@@ -2,7 +2,7 @@
 
 Reference: MiniGPT4FineTuneAgent.train (agents/minigpt4_finetune_agent.py:142-195): uniform image noise
 (`maybe_add_noise`), `loss = model(batch)["loss"]` (MiniGPTBase.forward, minigpt_base.py:323-362; shifted
-cross-entropy modeling_llama.py:101-123), `loss.backward()`, gradient reduction across the data-parallel ranks
+cross-entropy modeling_llama.py:101-123 - WITHOUT its label_smoothing=0.1 so far), `loss.backward()`, gradient reduction across the data-parallel ranks
 (`xm.reduce_gradients`) and `torch.optim.AdamW` (create_optimizer :338-347; lr 1e-5, weight decay 0.05, betas
 (0.9, 0.999) in configs/train_configs/vqav2_finetuning_noise_*.yaml).  The ViT, the Q-Former and the Llama are
 frozen (base_model.py:162-172,238-240; minigpt4.py:111-117): the ONLY trainable tensors are llama_proj.weight / .bias

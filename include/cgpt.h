@@ -140,7 +140,8 @@ int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int3
 
 /* token_loss[r] = logsumexp(logits[r, :]) - logits[r, targets[r]] in fp32, 0 where targets[r] < 0 (ignore_index
  * -100); mean_count (nullable) = {mean over the counted rows, their number} by a fixed-order reduction.
- * CrossEntropyLoss(reduction='mean') of the training / validation forward (modeling_llama.py:101-123). */
+ * Plain CrossEntropyLoss(reduction='mean') of the training / validation forward (modeling_llama.py:101-123); the reference's
+ * subclass adds label_smoothing=0.1 there (:107), which these kernels do not apply yet. */
 int cgpt_ce_loss(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, float* token_loss,
                  float* mean_count, void* stream);
 

@@ -229,11 +229,14 @@ def generate_ids(sd, cfg, embeds, max_new_tokens=20, min_length=1, prefix="llama
 
 
 # ------------------------------------------------------------------ answer -> label adapter
-def lm_loss(sd, cfg, images, prefix_ids, suffix_ids, answers, prefix="llama_model."):
+def lm_loss(sd, cfg, images, prefix_ids, suffix_ids, answers, prefix="llama_model.", label_smoothing=0.0):
     """Training / validation forward of MiniGPTBase (minigpt_base.py:323-362): inputs = [bos+prompt | image | rest of
     the prompt | answer], targets = answer ids at the answer positions and -100 elsewhere, loss = the shifted
     CrossEntropyLoss(mean) of modeling_llama.py:101-123.  answers: LongTensor [B, na], -100 = right padding
-    (pad embedding fed, target ignored).  Returns (mean loss, per-token losses [B, na])."""
+    (pad embedding fed, target ignored).  Returns (mean loss, per-token losses [B, na]).
+    label_smoothing: the reference's subclass builds CrossEntropyLoss(label_smoothing=0.1) (modeling_llama.py:107);
+    0.1 reproduces a run of that file (tests/golden/ref_forward.pt), the default 0.0 is the stock transformers loss,
+    which is what libcgpt's cgpt_ce_loss / cgpt_ce_grad compute today (known gap)."""
     l = cfg.llm
     emb = sd[prefix + "model.embed_tokens.weight"]
     img = encode_img(sd, cfg, images)
@@ -246,12 +249,13 @@ def lm_loss(sd, cfg, images, prefix_ids, suffix_ids, answers, prefix="llama_mode
     targets = torch.full(embeds.shape[:2], -100, dtype=torch.long)
     targets[:, Lc:Lc + na] = answers
     shift_logits, shift_labels = logits[:, :-1].reshape(-1, l.vocab), targets[:, 1:].reshape(-1)
-    loss = F.cross_entropy(shift_logits, shift_labels, ignore_index=-100, reduction="mean")
-    tok = F.cross_entropy(shift_logits, shift_labels, ignore_index=-100, reduction="none").view(embeds.shape[0], -1)
+    loss = F.cross_entropy(shift_logits, shift_labels, ignore_index=-100, reduction="mean", label_smoothing=label_smoothing)
+    tok = F.cross_entropy(shift_logits, shift_labels, ignore_index=-100, reduction="none",
+                          label_smoothing=label_smoothing).view(embeds.shape[0], -1)
     return loss, tok[:, Lc - 1:Lc - 1 + na]
 
 
-def finetune_grads(sd, cfg, images, prefix_ids, suffix_ids, answers):
+def finetune_grads(sd, cfg, images, prefix_ids, suffix_ids, answers, label_smoothing=0.0):
     """loss.backward() of the fine-tune step (agents/minigpt4_finetune_agent.py:165-172) by torch autograd over the
     restated forward: only llama_proj.weight / .bias require grad (everything else is frozen, base_model.py:162-172,
     238-240; minigpt4.py:111-117).  Returns (loss, dW, db)."""
@@ -260,7 +264,7 @@ def finetune_grads(sd, cfg, images, prefix_ids, suffix_ids, answers):
     b = sd["llama_proj.bias"].detach().float().clone().requires_grad_(True)
     sd2["llama_proj.weight"], sd2["llama_proj.bias"] = W, b
     with torch.enable_grad():
-        loss, _ = lm_loss(sd2, cfg, images, prefix_ids, suffix_ids, answers)
+        loss, _ = lm_loss(sd2, cfg, images, prefix_ids, suffix_ids, answers, label_smoothing=label_smoothing)
         loss.backward()
     return loss.detach(), W.grad.detach(), b.grad.detach()
 

@@ -4,8 +4,10 @@ MiniGPTBase.forward -> preparing_embedding -> prompt_wrap -> concat_emb_input_ou
 
 Runs only in the build container (needs /root/reference, read-only).  Same shims and stub `self` as
 make_ref_generate_fixtures.py; in addition
-  * llama_model   this image's transformers.LlamaForCausalLM behind a wrapper that drops the `reduction` keyword (the
-                  reference's modeling_llama.py subclass adds it; 'mean' is the stock behaviour) and records the call
+  * llama_model   the reference's OWN LlamaForCausalLM subclass (modeling_llama.py, executed unmodified by path over this
+                  image's transformers 5.5 Llama; its loss is CrossEntropyLoss(label_smoothing=0.1), :107) on seeded
+                  weights, behind a recorder of the one call forward() makes; the stock class's loss on the same call is
+                  stored next to it
   * encode_img    oracle.model_oracle.encode_img on seeded images (the image tower is pinned separately,
                   make_ref_encode_img_fixture.py); the test regenerates the same embeddings
 So the fixture pins the GLUE of the fine-tune step's forward: BOS embedding first, prompt segments around <ImageHere>
@@ -39,27 +41,49 @@ CASES = [
 ]
 
 
-class LlamaSpy:
-    """stands in for the reference's LlamaForCausalLM subclass: same call, `reduction` dropped"""
+def load_reference_llama():
+    """graphs/models/minigpt4/models/modeling_llama.py by path: the subclass whose forward adds `reduction` and builds
+    CrossEntropyLoss(label_smoothing=0.1).  Two names it imports no longer exist in transformers 5 (docstring constants)."""
+    import importlib.util
+    import transformers.models.llama.modeling_llama as ml
+    import transformers.utils as tu
+    for name in ("LLAMA_INPUTS_DOCSTRING", "_CONFIG_FOR_DOC"):
+        if not hasattr(ml, name):
+            setattr(ml, name, "")
+    for name in ("add_start_docstrings_to_model_forward", "replace_return_docstrings"):
+        if not hasattr(tu, name):
+            setattr(tu, name, lambda *a, **k: (lambda f: f))
+    spec = importlib.util.spec_from_file_location("ref_modeling_llama",
+                                                  "/root/reference/graphs/models/minigpt4/models/modeling_llama.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.LlamaForCausalLM
 
-    def __init__(self, hf):
-        self.hf, self.base_model, self.calls = hf, hf.base_model, []
+
+class LlamaSpy:
+    """records the one call MiniGPTBase.forward makes and passes it to the reference's LlamaForCausalLM"""
+
+    def __init__(self, model):
+        self.model, self.base_model, self.calls = model, model.base_model, []
 
     def __call__(self, **kw):
-        assert kw.pop("reduction") == "mean"
         self.calls.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in kw.items()})
-        return self.hf(**kw)
+        return self.model(**kw)
 
 
 def main():
     ref = G0.load_reference().MiniGPTBase
+    RefLlama = load_reference_llama()
     out = {"reference": "MiniGPTBase.forward / preparing_embedding / prompt_wrap / concat_emb_input_output "
                         "(minigpt_base.py, executed unmodified)", "cases": []}
     for case in CASES:
         cfg = ModelConfig.tiny()
         cfg.llm = LlmConfig(hidden=64, layers=2, heads=4, inter=128, vocab=96)
         sd = random_state_dict(cfg, seed=case["seed"])
-        spy = LlamaSpy(hf_llama(cfg, sd))
+        hf = hf_llama(cfg, sd)                                   # stock transformers Llama on the seeded weights
+        ref_llama = RefLlama(hf.config).eval()                   # the reference's subclass, same weights
+        ref_llama.load_state_dict(hf.state_dict())
+        spy = LlamaSpy(ref_llama)
         B = len(case["answers"])
         images = torch.randn(B, 3, cfg.vit.img_size, cfg.vit.img_size, generator=torch.Generator().manual_seed(case["seed"]))
 
@@ -78,10 +102,13 @@ def main():
             res = ref.forward(stub, samples)
         assert res is not None and len(spy.calls) == 1, "the reference forward swallowed an exception"
         call = spy.calls[0]
-        out["cases"].append({"case": case, "images": images, "loss": float(res["loss"]),
+        assert call["reduction"] == "mean"
+        with torch.no_grad():                                    # the same call through the stock class: plain CE
+            plain = hf(inputs_embeds=call["inputs_embeds"], attention_mask=call["attention_mask"], labels=call["labels"]).loss
+        out["cases"].append({"case": case, "images": images, "loss": float(res["loss"]), "loss_stock_transformers": float(plain),
                              "attention_mask": call["attention_mask"], "labels": call["labels"],
                              "inputs_embeds": call["inputs_embeds"]})
-        print(case["name"], tuple(call["inputs_embeds"].shape), float(res["loss"]), call["labels"][-1].tolist()[-8:])
+        print(case["name"], tuple(call["inputs_embeds"].shape), float(res["loss"]), float(plain), call["labels"][-1].tolist()[-8:])
     torch.save(out, os.path.join(HERE, "ref_forward.pt"))
 
 

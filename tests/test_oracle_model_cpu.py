@@ -196,7 +196,8 @@ def test_encode_img_equals_the_reference_encode_img_run(name, cfg):
 def test_training_forward_equals_the_reference_forward_run(rec):
     """oracle.lm_loss (and the product's split_prompt / answer tokenisation) against a run of the reference's OWN
     MiniGPTBase.forward -> preparing_embedding -> prompt_wrap -> concat_emb_input_output (tests/golden/
-    make_ref_forward_fixture.py): the embeddings and labels handed to the Llama and the mean cross-entropy."""
+    make_ref_forward_fixture.py) over the reference's OWN LlamaForCausalLM subclass (modeling_llama.py): the embeddings
+    and labels handed to the Llama and its label-smoothed mean cross-entropy."""
     from certifiedgpt_b200.data import vqav2 as V
     from ref_generate_util import encode_special
     case = rec["case"]
@@ -211,8 +212,13 @@ def test_training_forward_equals_the_reference_forward_run(rec):
     assert all(r[-1] == cfg.llm.eos_id for r in rows)
     with torch.no_grad():
         loss, tok = mo.lm_loss(sd, cfg, rec["images"], prefix, suffix, answers)
+        smooth, _ = mo.lm_loss(sd, cfg, rec["images"], prefix, suffix, answers, label_smoothing=0.1)
         cond = mo.build_prompt_embeds(sd, cfg, mo.encode_img(sd, cfg, rec["images"]), prefix, suffix)
-    assert loss.item() == pytest.approx(rec["loss"], abs=2e-5)
+    # the reference's own LlamaForCausalLM subclass: CrossEntropyLoss(label_smoothing=0.1) (modeling_llama.py:107)
+    assert smooth.item() == pytest.approx(rec["loss"], abs=2e-5)
+    # the stock transformers loss on the same call = plain CE = what cgpt_ce_loss computes (known gap)
+    assert loss.item() == pytest.approx(rec["loss_stock_transformers"], abs=2e-5)
+    assert abs(rec["loss"] - rec["loss_stock_transformers"]) > 1e-3
     Lc = cond.shape[1]
     labels = torch.full((len(rows), Lc + na), -100, dtype=torch.long)
     labels[:, Lc:] = answers
