@@ -27,6 +27,11 @@ INSTRUCTION_TEMPLATES = ("[vqa] {}",
                          "[vqa] Based on the image, respond to this question with a short answer: {}")   # vqav2_dataset.py:39-42
 PROMPT_TEMPLATE = "[INST] {} [/INST]"           # configs: prompt_template of the minigpt4 / minigpt_v2 models
 END_SYM = "</s>"
+# The evaluation call site of MiniGPTBase.generate (agents/minigpt4_eval_agent.py:80-96): prepare_texts
+# (graphs/models/minigpt4/common/eval_utils.py:37-43) over CONV_VISION_minigptv2 (conversation/conversation.py:130-137,
+# roles "<s>[INST] " / " [/INST]", empty separator) on the questions of VQAv2TestDataset (vqav2_dataset.py:201).
+EVAL_QUESTION_TEMPLATE = "[vqa] Based on the image, respond to this question with a short answer: {}"
+EVAL_PROMPT_TEMPLATE = "<s>[INST] <Img><ImageHere></Img> {} [/INST]"
 
 
 class ImageProcessor:
@@ -119,6 +124,42 @@ class VQAv2Dataset:
         return {"image": d["image"], "question_id": d["question_id"],
                 "instruction_input": "<Img><ImageHere></Img> {} ".format(instruction), "answer": d["answer"],
                 "answer_weights": d["answer_weights"]}
+
+
+class VQAv2TestDataset:
+    """Questions-only evaluation split (vqav2_dataset.py:173-205): COCO_<split>2015 file names, the RAW question inside
+    the short-answer instruction (no text processor), no answers."""
+
+    def __init__(self, questions_paths, vis_paths, split="test", vis_processor=None):
+        self.vis_paths, self.split = vis_paths, split
+        self.vis_processor = vis_processor or ImageProcessor()
+        self.questions = []
+        for p in questions_paths:
+            q = json.load(open(p))
+            if isinstance(q, dict):
+                self.questions.extend(q["questions"])
+
+    def __len__(self):
+        return len(self.questions)
+
+    def image_path(self, image_id):
+        return os.path.join(self.vis_paths, f"COCO_{self.split}2015_{image_id:012d}.jpg")
+
+    def __getitem__(self, idx):
+        from PIL import Image
+        d = self.questions[idx]
+        return {"image": self.vis_processor(Image.open(self.image_path(d["image_id"]))),
+                "question": EVAL_QUESTION_TEMPLATE.format(d["question"]), "question_id": d["question_id"],
+                "img_id": d["image_id"]}
+
+
+def eval_prompt(question):
+    """The text the reference's evaluation loop hands to generate() for one dataset question (see EVAL_PROMPT_TEMPLATE).
+    It starts with the literal "<s>" of the conversation role AND get_context_emb adds the tokenizer's BOS to the first
+    segment (minigpt_base.py:79-82), so with a Llama tokenizer the prompt opens with two BOS ids:
+    `split_prompt(eval_prompt(q), encode, prompt_template="{}")` reproduces exactly that when `encode` maps the literal
+    "<s>" to the BOS id, as LlamaTokenizer does."""
+    return EVAL_PROMPT_TEMPLATE.format(question)
 
 
 def split_prompt(instruction_input, encode, bos_id=1, prompt_template=PROMPT_TEMPLATE):

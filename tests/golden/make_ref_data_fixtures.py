@@ -84,6 +84,12 @@ def main():
                                          "instruction_input": it["instruction_input"], "answer": it["answer"],
                                          "image": U.image_digest(it["image"]), "shape": list(it["image"].shape)})
             out["image_sizes"][str(size)] = rec
+        # evaluation split: VQAv2TestDataset (questions only, COCO_test2015 names, raw question in the instruction)
+        vis = procs.Blip2ImageTrainProcessor(image_size=56)
+        tds = dsm.VQAv2TestDataset([qp], vis, os.path.join(root, "test2015"), "test")
+        out["test_dataset"] = {"len": len(tds), "items": [
+            {"index": i, "question": it["question"], "question_id": it["question_id"], "img_id": it["img_id"],
+             "image": U.image_digest(it["image"])} for i, it in ((i, tds[i]) for i in range(3))]}
         # answer sampling frequencies of annotation 0 (confidence weights: red 14/16, dark red 2/16, blue 0)
         vis = procs.Blip2ImageTrainProcessor(image_size=56)
         ds = dsm.VQAv2Dataset(vis, text, [qp], img_dir, [ap], split="train")

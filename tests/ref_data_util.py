@@ -22,6 +22,12 @@ def build(root):
         arr = rng.integers(0, 256, size=(60 + 10 * i, 80, 3), dtype=np.uint8)
         with open(os.path.join(img_dir, f"COCO_train2014_{iid:012d}.jpg"), "wb") as f:
             Image.fromarray(arr).save(f, format="PNG")
+    test_dir = os.path.join(root, "test2015")
+    os.makedirs(test_dir, exist_ok=True)
+    for iid in IDS:                                        # same pixels under the evaluation split's file names
+        src = os.path.join(img_dir, f"COCO_train2014_{iid:012d}.jpg")
+        with open(src, "rb") as f, open(os.path.join(test_dir, f"COCO_test2015_{iid:012d}.jpg"), "wb") as g:
+            g.write(f.read())
     questions = {"questions": [{"question_id": 1000 + i, "image_id": iid, "question": q}
                                for i, (iid, q) in enumerate(zip(IDS, QUESTIONS))]}
     questions["questions"].append({"question_id": 7, "image_id": 9, "question": "unused"})

@@ -104,3 +104,37 @@ def test_text_processor_and_answer_sampling_equal_the_reference_run(fake_vqav2):
     qp, ap, img_dir = fake_vqav2
     ds = V.VQAv2Dataset([qp], [ap], img_dir, split="train", vis_processor=V.ImageProcessor(56), seed=3)
     assert [ds.get_data(0)["answer"] for _ in range(400)] == REF_DATA["answer_draws_seed3"]
+
+
+def test_eval_split_equals_the_reference_test_dataset_run(fake_vqav2):
+    """VQAv2TestDataset (questions only) against a run of the reference's own class on the same files."""
+    qp, _, img_dir = fake_vqav2
+    rec = REF_DATA["test_dataset"]
+    ds = V.VQAv2TestDataset([qp], os.path.join(os.path.dirname(img_dir), "test2015"), split="test",
+                            vis_processor=V.ImageProcessor(56))
+    assert len(ds) == rec["len"] == 4                       # no annotation filter on the evaluation split
+    for want in rec["items"]:
+        got = ds[want["index"]]
+        assert (got["question"], got["question_id"], got["img_id"]) == (want["question"], want["question_id"], want["img_id"])
+        dg = U.image_digest(got["image"])
+        assert dg["sumsq"] == pytest.approx(want["image"]["sumsq"], rel=1e-6)
+        assert np.allclose(dg["pooled"], want["image"]["pooled"], atol=1e-5)
+
+
+def test_eval_prompt_equals_the_reference_eval_call_site():
+    """eval_prompt + split_prompt against tests/golden/ref_prompt.json: the texts the reference's prepare_texts +
+    CONV_VISION_minigptv2 produce for generate(), and the token ids its get_context_emb requests (two BOS ids: the
+    tokenizer's and the literal "<s>" of the conversation role)."""
+    from ref_generate_util import encode_special
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_prompt.json")))
+    enc = lambda s: encode_special(s, ref["vocab"])
+    for q, dq, rec in zip(ref["questions"], ref["dataset_questions"], ref["prompts"]):
+        assert V.EVAL_QUESTION_TEMPLATE.format(q) == dq
+        text = V.eval_prompt(dq)
+        assert text == rec["text"]
+        prefix, suffix = V.split_prompt(text, enc, prompt_template="{}")
+        seg0, seg1 = rec["segments"]
+        assert seg0["add_special_tokens"] is True and seg1["add_special_tokens"] is False
+        assert prefix == seg0["ids"] and prefix[:2] == [1, 1]
+        assert suffix == seg1["ids"]
+        assert rec["rows"] == len(prefix) + 4 + len(suffix)
