@@ -25,8 +25,18 @@ MEAN = (0.48145466, 0.4578275, 0.40821073)     # base_processor.py:17
 STD = (0.26862954, 0.26130258, 0.27577711)     # base_processor.py:19
 INSTRUCTION_TEMPLATES = ("[vqa] {}",
                          "[vqa] Based on the image, respond to this question with a short answer: {}")   # vqav2_dataset.py:39-42
-PROMPT_TEMPLATE = "[INST] {} [/INST]"           # configs: prompt_template of the minigpt4 / minigpt_v2 models
+# Training-forward text conventions.  Two exist in the reference and both are pinned to runs of its forward
+# (tests/golden/ref_forward.pt):
+#   * chat style (defaults below): models that set `chat_template` wrap the instruction as "[INST] {} [/INST]" and end the
+#     answer with "</s>" (minigpt_base.py:282-283,295) - the convention the evaluation agent's conversation template
+#     (EVAL_PROMPT_TEMPLATE) matches;
+#   * the SHIPPED fine-tune configs (configs/train_configs/vqav2_finetuning_noise_*.yaml: arch minigpt4, end_sym "###"):
+#     MiniGPT4 defines no chat_template, so the dataset's instruction is fed RAW and the answer ends with "###"
+#     -> split_prompt(..., prompt_template=SHIPPED_PROMPT_TEMPLATE), finetune_items(..., end_sym=SHIPPED_END_SYM).
+PROMPT_TEMPLATE = "[INST] {} [/INST]"
 END_SYM = "</s>"
+SHIPPED_PROMPT_TEMPLATE = "{}"
+SHIPPED_END_SYM = "###"
 # The evaluation call site of MiniGPTBase.generate (agents/minigpt4_eval_agent.py:80-96): prepare_texts
 # (graphs/models/minigpt4/common/eval_utils.py:37-43) over CONV_VISION_minigptv2 (conversation/conversation.py:130-137,
 # roles "<s>[INST] " / " [/INST]", empty separator) on the questions of VQAv2TestDataset (vqav2_dataset.py:201).

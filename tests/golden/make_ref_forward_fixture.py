@@ -33,7 +33,19 @@ from certifiedgpt_b200.weights import random_state_dict  # noqa: E402
 from oracle import model_oracle as mo  # noqa: E402
 from ref_generate_util import CharTokenizer, hf_llama  # noqa: E402
 
+# style "v2_chat": chat_template set, prompt_template "[INST] {} [/INST]", end_sym "</s>" (the MiniGPT-v2 convention the
+# evaluation agent's conversation template matches).  style "shipped": the reference's own fine-tune configs
+# (configs/train_configs/vqav2_finetuning_noise_*.yaml: arch minigpt4, end_sym "###", prompt_template
+# '###Human: {} ###Assistant: '): MiniGPT4 defines no chat_template, so forward() feeds the dataset's instruction RAW
+# (minigpt_base.py:282-283) and the template only serves prompt_list, which instruction_input overrides (:274-279).
+STYLES = {
+    "v2_chat": dict(chat_template=True, prompt_template="[INST] {} [/INST]", end_sym="</s>"),
+    "shipped": dict(prompt_template="###Human: {} ###Assistant: ", end_sym="###"),
+}
+
 CASES = [
+    dict(name="shipped_config", seed=34, style="shipped", instruction="<Img><ImageHere></Img> [vqa] what color is the car ? ",
+         answers=["red", "dark red"]),
     dict(name="equal_answers", seed=31, instruction="<Img><ImageHere></Img> [vqa] what color is the car ? ", answers=["red", "big"]),
     dict(name="ragged_answers", seed=32, instruction="<Img><ImageHere></Img> [vqa] is it raining ? ", answers=["no", "dark red", "2"]),
     dict(name="single", seed=33, instruction="<Img><ImageHere></Img> [vqa] Based on the image, respond to this question with a short answer: how many dogs ? ",
@@ -93,8 +105,7 @@ def main():
             return e, torch.ones(e.shape[:2], dtype=torch.long)
         stub = types.SimpleNamespace(device=torch.device("cpu"), llama_model=spy, llama_tokenizer=CharTokenizer(cfg.llm.vocab),
                                      maybe_autocast=contextlib.nullcontext, encode_img=encode_img, prompt_list=[],
-                                     chat_template=True, prompt_template="[INST] {} [/INST]", end_sym="</s>",
-                                     max_txt_len=160, max_context_len=3800)
+                                     max_txt_len=160, max_context_len=3800, **STYLES[case.get("style", "v2_chat")])
         for fn in ("embed_tokens", "prompt_wrap", "concat_emb_input_output", "preparing_embedding"):
             setattr(stub, fn, functools.partial(getattr(ref, fn), stub))
         samples = {"image": images, "instruction_input": [case["instruction"]] * B, "answer": case["answers"]}

@@ -205,11 +205,15 @@ def test_training_forward_equals_the_reference_forward_run(rec):
     cfg.llm = LlmConfig(hidden=64, layers=2, heads=4, inter=128, vocab=96)
     sd = random_state_dict(cfg, seed=case["seed"])
     enc = lambda s: encode_special(s, cfg.llm.vocab)
-    prefix, suffix = V.split_prompt(case["instruction"], enc)               # wraps with "[INST] {} [/INST]"
-    rows = [enc(a + V.END_SYM) for a in case["answers"]]
+    if case.get("style") == "shipped":      # the reference's own fine-tune configs: raw instruction, answers end with "###"
+        template, end_sym = V.SHIPPED_PROMPT_TEMPLATE, V.SHIPPED_END_SYM
+    else:                                   # chat style: "[INST] {} [/INST]", "</s>"
+        template, end_sym = V.PROMPT_TEMPLATE, V.END_SYM
+    prefix, suffix = V.split_prompt(case["instruction"], enc, prompt_template=template)
+    rows = [enc(a + end_sym) for a in case["answers"]]
     na = max(len(r) for r in rows)
     answers = torch.tensor([r + [-100] * (na - len(r)) for r in rows])
-    assert all(r[-1] == cfg.llm.eos_id for r in rows)
+    assert all(r[-1] == cfg.llm.eos_id for r in rows) or case.get("style") == "shipped"
     with torch.no_grad():
         loss, tok = mo.lm_loss(sd, cfg, rec["images"], prefix, suffix, answers)
         smooth, _ = mo.lm_loss(sd, cfg, rec["images"], prefix, suffix, answers, label_smoothing=0.1)
