@@ -75,8 +75,12 @@ class MiniGPT4FineTuneAgent:
         if self.val_set is None:
             return float("inf")
         total, nb = 0.0, 0
-        for images, answers in self._batches(self.val_set):
-            total += float(self.trainer.forward(images.to(self.engine.dev), answers, 0.0).item())
+        nval = max(1, len(self.val_set) // self.batch_size)
+        for i, (images, answers) in enumerate(self._batches(self.val_set)):
+            # the reference's validation loop noises its inputs too (maybe_add_noise, :209); its own Philox streams
+            step = (1 << 30) + epoch * nval + i
+            total += float(self.trainer.forward(images.to(self.engine.dev), answers, self.noise_level, seed=self.seed,
+                                                step=step).item())
             nb += 1
         return total / nb if nb else float("inf")
 
