@@ -113,12 +113,14 @@ def _EXTRA_SIGS(vp, i64, i32, f32, f64, u64):
         "cgpt_gather_rows": [vp, i64, vp, i32, i32, i32, vp, i64, i32, i32, i32, i32, vp],
         "cgpt_cosine_rows": [vp, i64, i32, i32, vp, vp, vp],
         "cgpt_ce_loss": [vp, i64, i32, i32, vp, vp, vp, vp],
+        "cgpt_ce_loss_smooth": [vp, i64, i32, i32, vp, vp, vp, f32, vp],
         "cgpt_swiglu_fwd": [vp, vp, i64, i32, vp],
         "cgpt_swiglu_bwd": [vp, vp, vp, i64, i32, vp],
         "cgpt_rmsnorm_bwd": [vp, i64, vp, vp, i64, f32, i32, i32, vp, i64, i32, i32, i32, vp],
         "cgpt_rope_bwd_cast": [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
         "cgpt_attention_bwd": [vp, i64, vp, vp, i64, i32, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, f32, vp],
         "cgpt_ce_grad": [vp, i64, i32, i32, vp, vp, vp, i64, vp],
+        "cgpt_ce_grad_smooth": [vp, i64, i32, i32, vp, vp, vp, i64, f32, vp],
         "cgpt_cast_rows_f32_bf16": [vp, i64, vp, i64, i32, i32, i32, i32, i32, vp],
         "cgpt_transpose_bf16": [vp, i64, vp, i64, i32, i32, vp],
         "cgpt_colsum_bf16": [vp, i64, i32, i32, vp, vp],

@@ -92,7 +92,11 @@ int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int3
 
 int cgpt_ce_loss(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, float* token_loss,
                  float* mean_count, void* stream) {
-  return ce_loss(logits, ld, rows, cols, targets, token_loss, mean_count, (cudaStream_t)stream);
+  return ce_loss(logits, ld, rows, cols, targets, token_loss, mean_count, 0.f, (cudaStream_t)stream);
+}
+int cgpt_ce_loss_smooth(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, float* token_loss,
+                        float* mean_count, float label_smoothing, void* stream) {
+  return ce_loss(logits, ld, rows, cols, targets, token_loss, mean_count, label_smoothing, (cudaStream_t)stream);
 }
 
 int cgpt_cosine_rows(const float* feats, int64_t ld, int rows, int D, const float* target, float* scores,
@@ -143,7 +147,11 @@ int cgpt_attention_bwd(const void* q, int64_t ldq, const void* kcache, const voi
 }
 int cgpt_ce_grad(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, const float* mean_count,
                  void* dlogits, int64_t ldd, void* stream) {
-  return ce_grad(logits, ld, rows, cols, targets, mean_count, dlogits, ldd, (cudaStream_t)stream);
+  return ce_grad(logits, ld, rows, cols, targets, mean_count, dlogits, ldd, 0.f, (cudaStream_t)stream);
+}
+int cgpt_ce_grad_smooth(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, const float* mean_count,
+                        void* dlogits, int64_t ldd, float label_smoothing, void* stream) {
+  return ce_grad(logits, ld, rows, cols, targets, mean_count, dlogits, ldd, label_smoothing, (cudaStream_t)stream);
 }
 int cgpt_cast_rows_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, int row_period,
                             int row_stride, int row_offset, void* stream) {

@@ -172,6 +172,7 @@ struct cgpt_engine {
   int32_t* h_i32 = nullptr;   // [8]
   double* h_f64 = nullptr;    // [8]
   int last_steps = 0;
+  float label_smoothing = 0.f;   // cgpt_lm_loss: CrossEntropyLoss(label_smoothing) of modeling_llama.py:107 (set_option)
 };
 
 namespace cgpt {
@@ -1015,7 +1016,7 @@ int cgpt_lm_loss(cgpt_handle E, const void* patches, int B, const int32_t* answe
                      na, Tl, nq + ns - 1, s));
   CGPT_TRY(gemm(b.l_xn, Hd, E->head_w, B * na, c.llm_vocab, Hd, Epi(b.l_logits, c.llm_vocab, CGPT_DT_F32), s));
   CGPT_TRY(ce_loss(static_cast<const float*>(b.l_logits), c.llm_vocab, B * na, c.llm_vocab, answer_ids, out_token_loss,
-                   out_mean_count, s));
+                   out_mean_count, E->label_smoothing, s));
   return 0;
 }
 
@@ -1085,6 +1086,10 @@ int cgpt_set_option(cgpt_handle E, const char* key, int value) {
   CGPT_REQUIRE(E != nullptr && key != nullptr, "cgpt_set_option: null argument");
   if (!strcmp(key, "use_graphs")) E->c.use_graphs = value != 0;
   else if (!strcmp(key, "early_exit")) E->c.early_exit = value != 0;
+  else if (!strcmp(key, "label_smoothing_permille")) {
+    CGPT_REQUIRE(value >= 0 && value < 1000, "cgpt_set_option: label_smoothing_permille %d outside [0, 1000)", value);
+    E->label_smoothing = static_cast<float>(value) / 1000.f;
+  }
   else CGPT_REQUIRE(false, "cgpt_set_option: unknown key '%s'", key);
   return 0;
 }

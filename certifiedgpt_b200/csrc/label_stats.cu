@@ -410,10 +410,13 @@ int cosine_rows(const float* feats, long long ld, int rows, int D, const float* 
 
 
 // ------------------------------------------------------------------ language-model loss (modeling_llama.py:101-123)
-// loss[r] = logsumexp(logits[r, :]) - logits[r, target[r]]  (fp32; 0 and not counted when target[r] < 0 = ignore_index)
+// loss[r] = logsumexp(z) - (1 - eps) * z[target[r]] - eps * mean(z)   (z = logits[r, :], fp32; eps = label smoothing,
+// CrossEntropyLoss(label_smoothing=0.1) at modeling_llama.py:107; eps = 0 is the plain loss); 0 and not counted when
+// target[r] < 0 = ignore_index
 __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ logits, long long ld, int cols,
-                                                      const int* __restrict__ targets, float* __restrict__ loss) {
+                                                      const int* __restrict__ targets, float* __restrict__ loss, float eps) {
   __shared__ float red[8];
+  __shared__ float red2[8];
   const int r = blockIdx.x;
   const int t = targets[r];
   if (t < 0 || t >= cols) {          // uniform per block
@@ -421,10 +424,11 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
     return;
   }
   const float* row = logits + r * ld;
-  float mx = -INFINITY;
-  for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, row[c]);
+  float mx = -INFINITY, zs = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) { mx = fmaxf(mx, row[c]); zs += row[c]; }
   mx = warp_max(mx);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  zs = warp_sum(zs);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = mx; red2[threadIdx.x >> 5] = zs; }
   __syncthreads();
   mx = red[0];
 #pragma unroll
@@ -436,10 +440,10 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float tot = 0.f;
+    float tot = 0.f, ztot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tot += red[i];   // fixed order
-    loss[r] = logf(tot) + mx - row[t];
+    for (int i = 0; i < 8; ++i) { tot += red[i]; ztot += red2[i]; }   // fixed order
+    loss[r] = logf(tot) + mx - (1.f - eps) * row[t] - eps * (ztot / static_cast<float>(cols));
   }
 }
 // out[0] = mean of loss[r] over targets[r] >= 0 (CrossEntropyLoss reduction='mean'), out[1] = their count.
@@ -468,9 +472,10 @@ __global__ void __launch_bounds__(256) masked_mean_kernel(const float* __restric
 }
 
 int ce_loss(const float* logits, long long ld, int rows, int cols, const int* targets, float* token_loss,
-            float* mean_count, cudaStream_t stream) {
+            float* mean_count, float label_smoothing, cudaStream_t stream) {
   CGPT_REQUIRE(logits && targets && token_loss && rows > 0 && cols > 0, "ce_loss: bad arguments rows=%d cols=%d", rows, cols);
-  ce_rows_kernel<<<rows, 256, 0, stream>>>(logits, ld, cols, targets, token_loss);
+  CGPT_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, "ce_loss: label_smoothing %f outside [0, 1)", label_smoothing);
+  ce_rows_kernel<<<rows, 256, 0, stream>>>(logits, ld, cols, targets, token_loss, label_smoothing);
   CGPT_CHECK_CUDA(cudaGetLastError());
   count_launch();
   if (mean_count != nullptr) {

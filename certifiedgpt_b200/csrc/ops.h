@@ -37,7 +37,7 @@ int certify_tail(const long long* counts_sel, const long long* counts_est, int n
 int predict_tail(const long long* counts, int num_classes, double alpha, int* out_label,
                  double* out_stats, cudaStream_t stream);
 int ce_loss(const float* logits, long long ld, int rows, int cols, const int* targets, float* token_loss,
-            float* mean_count, cudaStream_t stream);
+            float* mean_count, float label_smoothing, cudaStream_t stream);
 int cosine_rows(const float* feats, long long ld, int rows, int D, const float* target, float* scores,
                 cudaStream_t stream);
 int norm_rows(const void* x, long long ldx, int in_dtype, const float* gamma, const float* beta,
@@ -65,7 +65,7 @@ int attention_bwd(const void* q, long long ldq, const void* kc, const void* vc, 
                   long long ldo, const void* dout, long long lddo, float* dqkv, int B, int H, int hd, int Tq, int Tk,
                   float scale, cudaStream_t s);
 int ce_grad(const float* logits, long long ld, int rows, int cols, const int* targets, const float* mean_count, void* dlogits,
-            long long ldd, cudaStream_t s);
+            long long ldd, float label_smoothing, cudaStream_t s);
 int cast_rows_f32_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols, int period, int stride,
                        int offset, cudaStream_t s);
 int transpose_bf16(const void* src, long long lds, void* dst, long long ldd, int rows, int cols, cudaStream_t s);

@@ -208,10 +208,11 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const __nv_bfloat16* __re
 }
 
 // ---------------------------------------------------------------- cross-entropy gradient
-// dlogits[r, :] = (softmax(logits[r, :]) - onehot(target[r])) / count ; rows with target < 0 get zeros
+// dlogits[r, :] = (softmax(logits[r, :]) - (1 - eps) * onehot(target[r]) - eps / cols) / count ; rows with target < 0 get
+// zeros (eps = label smoothing, modeling_llama.py:107)
 __global__ void __launch_bounds__(256) ce_grad_kernel(const float* __restrict__ logits, long long ld, int cols,
                                                       const int* __restrict__ targets, const float* __restrict__ mean_count,
-                                                      __nv_bfloat16* __restrict__ dlogits, long long ldd) {
+                                                      __nv_bfloat16* __restrict__ dlogits, long long ldd, float eps) {
   __shared__ float red[8];
   const int r = blockIdx.x;
   const int t = targets[r];
@@ -239,9 +240,10 @@ __global__ void __launch_bounds__(256) ce_grad_kernel(const float* __restrict__ 
 #pragma unroll
   for (int i = 0; i < 8; ++i) tot += red[i];
   const float inv = 1.f / (tot * mean_count[1]);
-  const float sub = 1.f / mean_count[1];
+  const float sub = (1.f - eps) / mean_count[1];
+  const float uni = eps / (static_cast<float>(cols) * mean_count[1]);
   for (int c = threadIdx.x; c < cols; c += 256)
-    out[c] = __float2bfloat16(expf(row[c] - mx) * inv - (c == t ? sub : 0.f));
+    out[c] = __float2bfloat16(expf(row[c] - mx) * inv - (c == t ? sub : 0.f) - uni);
 }
 
 // ---------------------------------------------------------------- small helpers
@@ -347,9 +349,11 @@ int attention_bwd(const void* q, long long ldq, const void* kc, const void* vc, 
   LAUNCH_OK();
 }
 int ce_grad(const float* logits, long long ld, int rows, int cols, const int* targets, const float* mean_count, void* dlogits,
-            long long ldd, cudaStream_t s) {
+            long long ldd, float label_smoothing, cudaStream_t s) {
   CGPT_REQUIRE(logits && targets && mean_count && dlogits && rows > 0 && cols > 0, "ce_grad: bad arguments");
-  ce_grad_kernel<<<rows, 256, 0, s>>>(logits, ld, cols, targets, mean_count, static_cast<__nv_bfloat16*>(dlogits), ldd);
+  CGPT_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, "ce_grad: label_smoothing %f outside [0, 1)", label_smoothing);
+  ce_grad_kernel<<<rows, 256, 0, s>>>(logits, ld, cols, targets, mean_count, static_cast<__nv_bfloat16*>(dlogits), ldd,
+                                      label_smoothing);
   LAUNCH_OK();
 }
 int cast_rows_f32_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols, int period, int stride,

@@ -395,7 +395,7 @@ class NativeMiniGPT4Engine:
 
     @torch.no_grad()
     def lm_loss(self, images, answers, noise_level=0.0, *, noise_kind=L.NOISE_UNIFORM, noise_space=L.SPACE_NORMALIZED,
-                seed=0, step=0, mean=L.BLIP_MEAN, std=L.BLIP_STD):
+                seed=0, step=0, mean=L.BLIP_MEAN, std=L.BLIP_STD, label_smoothing=0.1):
         """Teacher-forced LM loss of the fine-tune / validation forward (MiniGPTBase.forward, minigpt_base.py:323-362;
         modeling_llama.py:101-123) for B different images [B,3,S,S] with answers [B, na] (int, -100 = padding).
         Noise as in MiniGPT4FineTuneAgent.maybe_add_noise (agents/minigpt4_finetune_agent.py:142-148:
@@ -414,6 +414,7 @@ class NativeMiniGPT4Engine:
         ans = answers.to(device=self.dev, dtype=torch.int32).contiguous()
         tok = torch.empty(B * na, dtype=torch.float32, device=self.dev)
         mc = torch.empty(2, dtype=torch.float32, device=self.dev)
+        self.set_option("label_smoothing_permille", int(round(1000 * label_smoothing)))   # modeling_llama.py:107
         L.check(self._lib.cgpt_lm_loss(self._h, L.ptr(patches), B, L.ptr(ans), na, L.ptr(tok), L.ptr(mc), L.stream_ptr()))
         return mc[0], tok.view(B, na)
 

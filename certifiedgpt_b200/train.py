@@ -2,7 +2,7 @@
 
 Reference: MiniGPT4FineTuneAgent.train (agents/minigpt4_finetune_agent.py:142-195): uniform image noise
 (`maybe_add_noise`), `loss = model(batch)["loss"]` (MiniGPTBase.forward, minigpt_base.py:323-362; shifted
-cross-entropy modeling_llama.py:101-123 - WITHOUT its label_smoothing=0.1 so far), `loss.backward()`, gradient reduction across the data-parallel ranks
+cross-entropy with label_smoothing=0.1, modeling_llama.py:101-123), `loss.backward()`, gradient reduction across the data-parallel ranks
 (`xm.reduce_gradients`) and `torch.optim.AdamW` (create_optimizer :338-347; lr 1e-5, weight decay 0.05, betas
 (0.9, 0.999) in configs/train_configs/vqav2_finetuning_noise_*.yaml).  The ViT, the Q-Former and the Llama are
 frozen (base_model.py:162-172,238-240; minigpt4.py:111-117): the ONLY trainable tensors are llama_proj.weight / .bias
@@ -35,8 +35,9 @@ class LlamaProjTrainer:
     `max_batch` images with up to `max_answer` answer tokens."""
 
     def __init__(self, engine: MiniGPT4Engine, *, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05,
-                 max_batch=4, max_answer=8, process_group=None):
+                 max_batch=4, max_answer=8, process_group=None, label_smoothing=0.1):
         self.eng = engine
+        self.label_smoothing = float(label_smoothing)   # CrossEntropyLoss(label_smoothing=0.1), modeling_llama.py:107
         self.cfg, self.dev, self.w = engine.cfg, engine.dev, engine.w
         self.lr, self.betas, self.eps, self.wd = float(lr), betas, float(eps), float(weight_decay)
         self.process_group = process_group
@@ -159,7 +160,8 @@ class LlamaProjTrainer:
         logits = L.gemm(xl, w["llm.head"], out_dtype=torch.float32)
         tok = torch.empty(R, dtype=torch.float32, device=self.dev)
         mc = torch.empty(2, dtype=torch.float32, device=self.dev)
-        self._ck(lib.cgpt_ce_loss(L.ptr(logits), logits.stride(0), R, l.vocab, L.ptr(ans), L.ptr(tok), L.ptr(mc), L.stream_ptr()))
+        self._ck(lib.cgpt_ce_loss_smooth(L.ptr(logits), logits.stride(0), R, l.vocab, L.ptr(ans), L.ptr(tok), L.ptr(mc),
+                                         self.label_smoothing, L.stream_ptr()))
         self.last = dict(B=B, na=na, Tl=Tl, M=M, R=R, gat=gat, logits=logits, ans=ans, mc=mc, tok=tok.view(B, na))
         return mc[0]
 
@@ -175,8 +177,8 @@ class LlamaProjTrainer:
         dx, dxb, dact, dgu, dh, datt, dqkv, dqkvb = (buf[k][:M] for k in ("dx", "dxb", "dact", "dgu", "dh", "datt", "dqkv", "dqkvb"))
         # loss -> logits -> last hidden state
         dlog = torch.empty(R, l.vocab, dtype=torch.bfloat16, device=self.dev)
-        self._ck(lib.cgpt_ce_grad(L.ptr(st["logits"]), st["logits"].stride(0), R, l.vocab, L.ptr(st["ans"]), L.ptr(st["mc"]),
-                                  L.ptr(dlog), dlog.stride(0), L.stream_ptr()))
+        self._ck(lib.cgpt_ce_grad_smooth(L.ptr(st["logits"]), st["logits"].stride(0), R, l.vocab, L.ptr(st["ans"]), L.ptr(st["mc"]),
+                                         L.ptr(dlog), dlog.stride(0), self.label_smoothing, L.stream_ptr()))
         dhl = L.gemm(dlog, wt["llm.head"], out_dtype=torch.float32)                       # [R, Hd]
         dx.zero_()
         self._rmsnorm_bwd(buf["res"][:M], w["llm.norm"], dhl, l.rms_eps, dx, R, st["gat"])    # res = output of the last layer

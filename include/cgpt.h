@@ -144,6 +144,10 @@ int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int3
  * subclass adds label_smoothing=0.1 there (:107), which these kernels do not apply yet. */
 int cgpt_ce_loss(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, float* token_loss,
                  float* mean_count, void* stream);
+/* the reference's loss: token_loss[r] = logsumexp(z) - (1 - eps) * z[target] - eps * mean(z), eps = label_smoothing
+ * (CrossEntropyLoss(label_smoothing=0.1), modeling_llama.py:107) */
+int cgpt_ce_loss_smooth(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, float* token_loss,
+                        float* mean_count, float label_smoothing, void* stream);
 
 /* scores[r] = cos(feats[r, :], target) in fp32 (one warp per row): the CLIP feature cosine of the black-box
  * attack loop (BASELINE.json configs[4]; README.md:62-64 - the reference ships no code for it) */
@@ -226,6 +230,9 @@ int cgpt_attention_bwd(const void* q, int64_t ldq, const void* kcache, const voi
 /* dlogits bf16 = (softmax(logits) - onehot(target)) / count, zero rows where target < 0; mean_count from cgpt_ce_loss */
 int cgpt_ce_grad(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, const float* mean_count,
                  void* dlogits, int64_t ldd, void* stream);
+/* dlogits = (softmax - (1 - eps) * onehot - eps / cols) / count: gradient of cgpt_ce_loss_smooth's mean */
+int cgpt_ce_grad_smooth(const float* logits, int64_t ld, int rows, int cols, const int32_t* targets, const float* mean_count,
+                        void* dlogits, int64_t ldd, float label_smoothing, void* stream);
 int cgpt_cast_rows_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, int row_period,
                             int row_stride, int row_offset, void* stream);
 int cgpt_transpose_bf16(const void* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream);
@@ -338,7 +345,7 @@ int cgpt_last_counts(cgpt_handle h, const int64_t** counts);
 /* decode steps run by the last batch (< max_new_tokens when early_exit stopped the loop), or -1 */
 int cgpt_last_decode_steps(cgpt_handle h);
 /* run-time switches: "use_graphs" (0 = launch every kernel eagerly, e.g. for per-kernel timing),
- * "early_exit" */
+ * "early_exit", "label_smoothing_permille" (cgpt_lm_loss: 100 = the reference's label_smoothing=0.1) */
 int cgpt_set_option(cgpt_handle h, const char* key, int value);
 
 /* ---------------------------------------------------------------- the one collective on the path

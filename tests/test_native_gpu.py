@@ -237,7 +237,7 @@ def test_lm_loss_forward_matches_oracle(name, cfg):
     V = cfg.llm.vocab
     answers = torch.tensor([[7, 9, 2, -100], [11, 2, -100, -100], [V - 1, 5, 6, 2], [3, 2, -100, -100], [8, 8, 8, 2]])
     loss, tok = nat.lm_loss(images.cuda(), answers, 0.0)
-    ref_loss, ref_tok = mo.lm_loss(sd, cfg, images, py.prefix_ids, py.suffix_ids, answers)
+    ref_loss, ref_tok = mo.lm_loss(sd, cfg, images, py.prefix_ids, py.suffix_ids, answers, label_smoothing=0.1)
     assert abs(loss.item() - ref_loss.item()) < 2e-2 * max(1.0, ref_loss.item())
     assert (tok.cpu() - ref_tok).abs().max().item() < 5e-2 * max(1.0, ref_tok.max().item())
     assert (tok.cpu()[answers < 0] == 0).all()
@@ -247,7 +247,7 @@ def test_lm_loss_forward_matches_oracle(name, cfg):
     noisy = torch.stack([L.noise_image(images[b].cuda().contiguous(), 1, lvl, seed=3, stream_id=5, first_sample=b,
                                        noise_kind=L.NOISE_UNIFORM)[0] for b in range(B)]).cpu()
     assert (noisy - images).min() >= 0 and (noisy - images).max() < lvl
-    ref_n, _ = mo.lm_loss(sd, cfg, noisy, py.prefix_ids, py.suffix_ids, answers)
+    ref_n, _ = mo.lm_loss(sd, cfg, noisy, py.prefix_ids, py.suffix_ids, answers, label_smoothing=0.1)
     assert abs(loss_n.item() - ref_n.item()) < 2e-2 * max(1.0, ref_n.item())
     # the generate path still works afterwards (the loss pass wrote answer K/V into the cache rows decode reuses)
     x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(3)).cuda()

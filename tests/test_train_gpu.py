@@ -129,6 +129,17 @@ def test_ce_grad_transpose_colsum_cast_adamw():
     F.cross_entropy(x, tg.long(), ignore_index=-100).backward()
     assert (dl.float() - x.grad).abs().max().item() < 1e-2 * x.grad.abs().max().item()
     assert (dl[2] == 0).all()
+    # the reference's label-smoothed loss (CrossEntropyLoss(label_smoothing=0.1), modeling_llama.py:107) and its gradient
+    L.check(h.cgpt_ce_loss_smooth(L.ptr(logits), V, R, V, L.ptr(tg), L.ptr(tok), L.ptr(mc), 0.1, L.stream_ptr()))
+    L.check(h.cgpt_ce_grad_smooth(L.ptr(logits), V, R, V, L.ptr(tg), L.ptr(mc), L.ptr(dl), V, 0.1, L.stream_ptr()))
+    x = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(x, tg.long(), ignore_index=-100, label_smoothing=0.1)
+    ref.backward()
+    assert abs(mc[0].item() - ref.item()) < 1e-4 and mc[1].item() == R - 1
+    ref_tok = F.cross_entropy(logits, tg.long(), ignore_index=-100, label_smoothing=0.1, reduction="none")
+    assert (tok - ref_tok).abs().max().item() < 1e-4
+    assert (dl.float() - x.grad).abs().max().item() < 1e-2 * x.grad.abs().max().item()
+    assert (dl[2] == 0).all()
     # transpose / column sum / gathered cast
     a = torch.randn(45, 70, device="cuda", generator=g).bfloat16()
     at = torch.zeros(70, 48, device="cuda", dtype=torch.bfloat16)
@@ -176,7 +187,7 @@ def test_finetune_gradients_match_oracle_autograd(name, cfg):
     loss = tr.forward(images.cuda(), answers, 0.0)
     gW, gb = tr.backward()
     torch.cuda.synchronize()
-    ref_loss, rW, rb = mo.finetune_grads(sd, cfg, images, eng.prefix_ids, eng.suffix_ids, answers)
+    ref_loss, rW, rb = mo.finetune_grads(sd, cfg, images, eng.prefix_ids, eng.suffix_ids, answers, label_smoothing=0.1)
     assert abs(loss.item() - ref_loss.item()) < 2e-2 * max(1.0, ref_loss.item())
     for got, ref, nm in ((gW.cpu(), rW, "weight"), (gb.cpu(), rb, "bias")):
         cos = F.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
