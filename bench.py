@@ -118,23 +118,9 @@ class ClockSampler:
 def aliased_full_state_dict(cfg):
     """Full-size fp32 random weights for the CPU oracle with every transformer layer ALIASING
     layer 0's tensors: identical shapes, FLOPs and bytes per layer, a fraction of the init time and
-    RAM (timing sample only; parity tests never use this)."""
-    import copy
-    from certifiedgpt_b200.weights import random_state_dict
-    c1 = copy.deepcopy(cfg)
-    c1.vit.depth, c1.qf.layers, c1.llm.layers = 1, min(cfg.qf.layers, 2), 1
-    sd = random_state_dict(c1, seed=0)
-    for i in range(1, cfg.vit.depth):
-        for k in [k for k in sd if k.startswith("visual_encoder.blocks.0.")]:
-            sd[k.replace("blocks.0.", f"blocks.{i}.")] = sd[k]
-    for i in range(2, cfg.qf.layers):
-        src = i % 2
-        for k in [k for k in sd if k.startswith(f"Qformer.bert.encoder.layer.{src}.")]:
-            sd[k.replace(f"layer.{src}.", f"layer.{i}.")] = sd[k]
-    for i in range(1, cfg.llm.layers):
-        for k in [k for k in sd if k.startswith("llama_model.model.layers.0.")]:
-            sd[k.replace("layers.0.", f"layers.{i}.")] = sd[k]
-    return sd
+    RAM (timing sample only)."""
+    from certifiedgpt_b200.weights import aliased_state_dict
+    return aliased_state_dict(cfg, seed=0)
 
 
 def cpu_reference_runner(cfg, max_new_tokens):

@@ -105,12 +105,13 @@ def _EXTRA_SIGS(vp, i64, i32, f32, f64, u64):
         "cgpt_argmax_rows": [vp, i32, i32, i64, i32, vp, vp, vp],
         "cgpt_label_hist": [vp, i32, i32, vp, vp, vp],
         "cgpt_certify_tail": [vp, vp, i32, i64, f64, f64, vp, vp, vp],
+        "cgpt_certify_tail_lut": [vp, vp, i32, i64, f64, f64, vp, vp, vp, vp],
         "cgpt_predict_tail": [vp, i32, f64, vp, vp, vp],
         "cgpt_greedy_step": [vp, i32, vp, vp, i32, i32, i32, i32, vp, vp],
         "cgpt_norm_rows": [vp, i64, i32, vp, vp, f32, i32, i32, vp, i64, i32, i32, i32, i32, i32, vp],
         "cgpt_attention": [C.POINTER(AttnArgs), vp],
         "cgpt_rope_split": [vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, i32, i32, vp],
-        "cgpt_gather_rows": [vp, i64, vp, i32, i32, i32, vp, i64, i32, i32, i32, i32, vp],
+        "cgpt_gather_rows": [vp, i64, vp, i32, i32, i32, vp, i64, i32, i32, i32, i32, i32, vp],
         "cgpt_cosine_rows": [vp, i64, i32, i32, vp, vp, vp],
         "cgpt_ce_loss": [vp, i64, i32, i32, vp, vp, vp, vp],
         "cgpt_ce_loss_smooth": [vp, i64, i32, i32, vp, vp, vp, f32, vp],
@@ -340,14 +341,52 @@ def label_hist(labels, counts, invalid=None):
     return counts
 
 
-def certify_tail(counts_sel, counts_est, n, alpha, sigma):
-    """Device tail of Smooth.certify; returns (label_dev int32[2], stats_dev f64[3])."""
+_RADIUS_LUTS = {}
+
+
+def radius_lut_host(n, alpha):
+    """float64 [2*(n+1)]: pABar(nA) = Smooth._lower_confidence_bound(nA, n, alpha) and norm.ppf(pABar(nA)), nA = 0..n,
+    by the SciPy calls the reference makes once per image on the host (smoothing.py:55,117:
+    proportion_confint(NA, N, alpha=2*alpha, method="beta")[0] is beta.ppf(alpha, NA, N-NA+1) with 0 at NA = 0;
+    radius = sigma * norm.ppf(pABar)).  Tabulated once per (n, alpha); the Monte-Carlo loop itself never touches the
+    host.  Entries with pABar < 0.5 keep ppf = 0 (the reference abstains there and never evaluates it)."""
+    import numpy as np
+    from scipy.stats import beta, norm
+    n = int(n)
+    na = np.arange(1, n + 1, dtype=np.int64)
+    pab = np.zeros(n + 1, dtype=np.float64)
+    pab[1:] = beta.ppf(float(alpha), na, n - na + 1)
+    ppf = np.zeros(n + 1, dtype=np.float64)
+    ok = pab >= 0.5
+    ppf[ok] = norm.ppf(pab[ok])
+    return np.concatenate([pab, ppf])
+
+
+def radius_lut(n, alpha, device):
+    """Device copy of `radius_lut_host` (cached per (n, alpha, device))."""
+    dev = torch.device(device)
+    key = (int(n), float(alpha), dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    t = _RADIUS_LUTS.get(key)
+    if t is None:
+        t = torch.from_numpy(radius_lut_host(n, alpha)).to(dev)
+        _RADIUS_LUTS[key] = t
+    return t
+
+
+def certify_tail(counts_sel, counts_est, n, alpha, sigma, lut=None):
+    """Device tail of Smooth.certify; returns (label_dev int32[2], stats_dev f64[3]).  lut: `radius_lut(n, alpha)`
+    for a pABar / radius bit-identical to the reference's SciPy tail; None = device bisection + AS241."""
     lib = load()
     assert counts_sel.dtype == torch.int64 and counts_est.dtype == torch.int64
     lab = torch.empty(2, dtype=torch.int32, device=counts_sel.device)
     st = torch.empty(3, dtype=torch.float64, device=counts_sel.device)
-    check(lib.cgpt_certify_tail(ptr(counts_sel), ptr(counts_est), counts_sel.numel(), int(n),
-                                float(alpha), float(sigma), ptr(lab), ptr(st), stream_ptr()))
+    if lut is not None:
+        assert lut.dtype == torch.float64 and lut.numel() == 2 * (int(n) + 1) and lut.is_cuda
+        check(lib.cgpt_certify_tail_lut(ptr(counts_sel), ptr(counts_est), counts_sel.numel(), int(n),
+                                        float(alpha), float(sigma), ptr(lut), ptr(lab), ptr(st), stream_ptr()))
+    else:
+        check(lib.cgpt_certify_tail(ptr(counts_sel), ptr(counts_est), counts_sel.numel(), int(n),
+                                    float(alpha), float(sigma), ptr(lab), ptr(st), stream_ptr()))
     return lab, st
 
 
@@ -410,7 +449,7 @@ def gather_rows(table, ids, rows, out, *, id_period=None, remap=None):
         id_period = ids.numel() if ids is not None else table.shape[0]
     rp, rs, ro = remap if remap is not None else (0, 0, 0)
     check(lib.cgpt_gather_rows(ptr(table), table.stride(0), ptr(ids), id_period, rows, D, ptr(out),
-                               out.stride(0), _dt(out), rp, rs, ro, stream_ptr()))
+                               out.stride(0), _dt(out), rp, rs, ro, table.shape[0], stream_ptr()))
     return out
 
 

@@ -82,7 +82,14 @@ int cgpt_certify_tail(const int64_t* counts_sel, const int64_t* counts_est, int 
                       int64_t n, double alpha, double sigma, int32_t* out_label,
                       double* out_stats, void* stream) {
   return certify_tail((const long long*)counts_sel, (const long long*)counts_est, num_classes, n,
-                      alpha, sigma, out_label, out_stats, (cudaStream_t)stream);
+                      alpha, sigma, nullptr, out_label, out_stats, (cudaStream_t)stream);
+}
+int cgpt_certify_tail_lut(const int64_t* counts_sel, const int64_t* counts_est, int num_classes,
+                          int64_t n, double alpha, double sigma, const double* lut, int32_t* out_label,
+                          double* out_stats, void* stream) {
+  CGPT_REQUIRE(lut != nullptr, "cgpt_certify_tail_lut: null table");
+  return certify_tail((const long long*)counts_sel, (const long long*)counts_est, num_classes, n,
+                      alpha, sigma, lut, out_label, out_stats, (cudaStream_t)stream);
 }
 int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int32_t* out_label,
                       double* out_stats, void* stream) {
@@ -119,9 +126,9 @@ int cgpt_rope_split(void* qkv, int64_t ld, int rows, int T, int H, int head_dim,
 }
 int cgpt_gather_rows(const void* table, int64_t ldt, const int32_t* ids, int id_period, int rows, int D,
                      void* out, int64_t ldo, int out_dtype, int remap_period, int remap_stride,
-                     int remap_offset, void* stream) {
+                     int remap_offset, int table_rows, void* stream) {
   return gather_rows(table, ldt, ids, id_period, rows, D, out, ldo, out_dtype, remap_period, remap_stride,
-                     remap_offset, (cudaStream_t)stream);
+                     remap_offset, table_rows, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- fine-tune step kernels

@@ -172,6 +172,9 @@ struct cgpt_engine {
   int32_t* h_i32 = nullptr;   // [8]
   double* h_f64 = nullptr;    // [8]
   int last_steps = 0;
+  const double* lut = nullptr;   // cgpt_set_radius_lut: [pABar | Phi^-1(pABar)] for (lut_n, lut_alpha), caller-owned
+  long long lut_n = 0;
+  double lut_alpha = 0.0;
   float label_smoothing = 0.f;   // cgpt_lm_loss: CrossEntropyLoss(label_smoothing) of modeling_llama.py:107 (set_option)
 };
 
@@ -432,7 +435,7 @@ int qformer_forward(Engine* E, const void* image_embeds, int B, void* out_h, cud
   const int M = B * nq;
   const long long ldckv = static_cast<long long>(E->n_cross) * 2 * Hd;
   void* h = out_h;
-  CGPT_TRY(gather_rows(E->qf_q0, Hd, nullptr, nq, M, Hd, h, Hd, CGPT_DT_BF16, 0, 0, 0, s));
+  CGPT_TRY(gather_rows(E->qf_q0, Hd, nullptr, nq, M, Hd, h, Hd, CGPT_DT_BF16, 0, 0, 0, nq, s));
   CGPT_TRY(gemm(image_embeds, D, E->ckv_w, B * T, static_cast<int>(ldckv), D,
                 Epi(b.q_ckv, ldckv, CGPT_DT_BF16).bias(E->ckv_b), s));
   const float scale = 1.0f / sqrtf(static_cast<float>(E->qhd));
@@ -527,15 +530,15 @@ int build_prefix(Engine* E, cudaStream_t s) {
   CGPT_CHECK_CUDA(cudaMemsetAsync(b.kc, 0, cache_bytes, s));
   CGPT_CHECK_CUDA(cudaMemsetAsync(b.vc, 0, cache_bytes, s));
   if (P == 0) return 0;
-  CGPT_TRY(gather_rows(E->emb, Hd, E->prefix_ids, P, P, Hd, b.l_res, Hd, CGPT_DT_F32, 0, 0, 0, s));
+  CGPT_TRY(gather_rows(E->emb, Hd, E->prefix_ids, P, P, Hd, b.l_res, Hd, CGPT_DT_F32, 0, 0, 0, c.llm_vocab, s));
   CGPT_TRY(llm_layers(E, P, P, 1, b.l_res, b.l_xn, b.l_qkv, b.l_att, b.l_act, b.kp, b.vp,
                       static_cast<long long>(P) * Hd, 0, 0, P, 0, s));
   const long long layer_stride = static_cast<long long>(E->ws_B) * E->cache_rows * Hd;
   for (int i = 0; i < c.llm_layers; ++i) {
     CGPT_TRY(gather_rows(bf(b.kp) + static_cast<long long>(i) * P * Hd, Hd, nullptr, P, E->ws_B * P, Hd,
-                         bf(b.kc) + i * layer_stride, Hd, CGPT_DT_BF16, P, E->cache_rows, 0, s));
+                         bf(b.kc) + i * layer_stride, Hd, CGPT_DT_BF16, P, E->cache_rows, 0, P, s));
     CGPT_TRY(gather_rows(bf(b.vp) + static_cast<long long>(i) * P * Hd, Hd, nullptr, P, E->ws_B * P, Hd,
-                         bf(b.vc) + i * layer_stride, Hd, CGPT_DT_BF16, P, E->cache_rows, 0, s));
+                         bf(b.vc) + i * layer_stride, Hd, CGPT_DT_BF16, P, E->cache_rows, 0, P, s));
   }
   return 0;
 }
@@ -565,7 +568,7 @@ int llm_prefill_first(Engine* E, const void* qf_out, int B, cudaStream_t s) {
   CGPT_TRY(gemm(qf_out, c.qf_hidden, E->proj_w, B * nq, Hd, c.qf_hidden,
                 Epi(b.l_res, Hd, CGPT_DT_F32).bias(E->proj_b).remap(nq, Tp, 0), s));
   if (ns > 0)
-    CGPT_TRY(gather_rows(E->emb, Hd, E->suffix_ids, ns, B * ns, Hd, b.l_res, Hd, CGPT_DT_F32, ns, Tp, nq, s));
+    CGPT_TRY(gather_rows(E->emb, Hd, E->suffix_ids, ns, B * ns, Hd, b.l_res, Hd, CGPT_DT_F32, ns, Tp, nq, c.llm_vocab, s));
   // the last layer only needs the last prompt position of every sample (CGPT_NO_LAST_PRUNE=1: A/B switch)
   static const bool no_prune = getenv("CGPT_NO_LAST_PRUNE") != nullptr;
   const bool prune = Tp > 1 && !no_prune;
@@ -592,7 +595,7 @@ int llm_decode_step(Engine* E, int B, int t, cudaStream_t s) {
   const long long layer_stride = static_cast<long long>(E->ws_B) * E->cache_rows * Hd;
   const int row = E->P + E->Tp + t - 1;
   CGPT_TRY(copy_col_u32(b.cur, 1, b.ids + (t - 1), mn, B, s));
-  CGPT_TRY(gather_rows(E->emb, Hd, b.cur, B, B, Hd, b.l_res, Hd, CGPT_DT_F32, 0, 0, 0, s));
+  CGPT_TRY(gather_rows(E->emb, Hd, b.cur, B, B, Hd, b.l_res, Hd, CGPT_DT_F32, 0, 0, 0, c.llm_vocab, s));
   const int decode = ((E->lhd == 32 || E->lhd == 64 || E->lhd == 128) && c.llm_heads % 4 == 0) ? 1 : 0;
   CGPT_TRY(llm_layers(E, B, 1, B, b.l_res, b.l_xn, b.l_qkv, b.l_att, b.l_act, b.kc, b.vc, layer_stride, row, row,
                       E->cache_rows, decode, s));
@@ -975,10 +978,12 @@ int cgpt_llm_prefill_decode(cgpt_handle E, const void* queries, int B, int32_t* 
   return 0;
 }
 
-// clamp(ids, 0): -100 (ignored target) -> pad id 0 for the embedding lookup
-__global__ void clamp_ids_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int n, int pad_id) {
+// ids outside [0, vocab) -> pad id for the embedding lookup: -100 (ignored target), and ids >= vocab, which the loss
+// kernel does not score either (ce_rows_kernel) - callers validate user-supplied answers (native.py, train.py)
+__global__ void clamp_ids_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int n, int pad_id,
+                                 int vocab) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[i] < 0 ? pad_id : src[i];
+  if (i < n) dst[i] = (src[i] < 0 || src[i] >= vocab) ? pad_id : src[i];
 }
 
 int cgpt_lm_loss(cgpt_handle E, const void* patches, int B, const int32_t* answer_ids, int na, float* out_token_loss,
@@ -1002,12 +1007,12 @@ int cgpt_lm_loss(cgpt_handle E, const void* patches, int B, const int32_t* answe
   CGPT_TRY(gemm(b.q_h, c.qf_hidden, E->proj_w, B * nq, Hd, c.qf_hidden,
                 Epi(b.l_res, Hd, CGPT_DT_F32).bias(E->proj_b).remap(nq, Tl, 0), s));
   if (ns > 0)
-    CGPT_TRY(gather_rows(E->emb, Hd, E->suffix_ids, ns, B * ns, Hd, b.l_res, Hd, CGPT_DT_F32, ns, Tl, nq, s));
+    CGPT_TRY(gather_rows(E->emb, Hd, E->suffix_ids, ns, B * ns, Hd, b.l_res, Hd, CGPT_DT_F32, ns, Tl, nq, c.llm_vocab, s));
   int32_t* ids = b.ids;                                        // [B*na] <= ws_B * max_new_tokens
-  clamp_ids_kernel<<<(B * na + 255) / 256, 256, 0, s>>>(answer_ids, ids, B * na, c.pad_id);
+  clamp_ids_kernel<<<(B * na + 255) / 256, 256, 0, s>>>(answer_ids, ids, B * na, c.pad_id, c.llm_vocab);
   CGPT_CHECK_CUDA(cudaGetLastError());
   count_launch();
-  CGPT_TRY(gather_rows(E->emb, Hd, ids, B * na, B * na, Hd, b.l_res, Hd, CGPT_DT_F32, na, Tl, nq + ns, s));
+  CGPT_TRY(gather_rows(E->emb, Hd, ids, B * na, B * na, Hd, b.l_res, Hd, CGPT_DT_F32, na, Tl, nq + ns, c.llm_vocab, s));
   // the KV cache has P + Tp + max_new rows per sample: rows [P, P + Tl) are (re)written here
   CGPT_TRY(llm_layers(E, M, Tl, B, b.l_res, b.l_xn, b.l_qkv, b.l_att, b.l_act, b.kc, b.vc, layer_stride, P, P,
                       E->cache_rows, 0, s));
@@ -1043,7 +1048,8 @@ int cgpt_certify(cgpt_handle E, const float* x, const cgpt_noise_spec* noise, in
   // ONE sharded pass over [0, n0 + n), two count vectors, one all-reduce (smoothing.py:44,48)
   CGPT_TRY(sample_noise(E, x, noise, 0, n0 + n, batch_size, n0, rank, world, comm, E->b.counts, nullptr, s));
   const int nc = E->c.num_classes;
-  CGPT_TRY(certify_tail(E->b.counts, E->b.counts + nc, nc, n, alpha, noise->sigma, E->b.tail_label,
+  const double* lut = (E->lut != nullptr && E->lut_n == n && E->lut_alpha == alpha) ? E->lut : nullptr;
+  CGPT_TRY(certify_tail(E->b.counts, E->b.counts + nc, nc, n, alpha, noise->sigma, lut, E->b.tail_label,
                         E->b.tail_stats, s));
   CGPT_CHECK_CUDA(cudaMemcpyAsync(E->h_i32, E->b.tail_label, 2 * 4, cudaMemcpyDeviceToHost, s));
   CGPT_CHECK_CUDA(cudaMemcpyAsync(E->h_f64, E->b.tail_stats, 3 * 8, cudaMemcpyDeviceToHost, s));
@@ -1055,6 +1061,15 @@ int cgpt_certify(cgpt_handle E, const float* x, const cgpt_noise_spec* noise, in
     out_detail[1] = E->h_f64[1];
     out_detail[2] = E->h_f64[2];
   }
+  return 0;
+}
+
+int cgpt_set_radius_lut(cgpt_handle E, int64_t n, double alpha, const double* lut) {
+  CGPT_REQUIRE(E != nullptr, "cgpt_set_radius_lut: null handle");
+  CGPT_REQUIRE(lut == nullptr || (n > 0 && alpha > 0.0 && alpha < 1.0), "cgpt_set_radius_lut: bad (n, alpha)");
+  E->lut = lut;
+  E->lut_n = n;
+  E->lut_alpha = alpha;
   return 0;
 }
 

@@ -67,15 +67,22 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
   const float* row = logits + static_cast<long long>(r) * ld;
   float best = -INFINITY, second = -INFINITY;
   int bi = 0x7fffffff;
+  // (v, c) beats (b, i): larger value, lowest index on ties; NaN counts as the maximum (torch.argmax), so a
+  // poisoned row still yields an index inside [0, cols) - the next decode step gathers an embedding row with it
+  auto beats = [](float v, int c, float b, int i) {
+    const bool vn = v != v, bn = b != b;
+    if (vn || bn) return vn && (!bn || c < i);
+    return v > b || (v == b && c < i);
+  };
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
     float v = row[c];
     if (c == suppress_col) v = -INFINITY;
-    if (v > best || (v == best && c < bi)) { second = best; best = v; bi = c; }
+    if (beats(v, c, best, bi)) { second = best; best = v; bi = c; }
     else if (v > second) second = v;
   }
   // warp then block reduction of (best, idx, second); lowest index wins ties (torch.argmax)
-  auto merge = [](float& b1, int& i1, float& s1, float b2, int i2, float s2) {
-    if (b2 > b1 || (b2 == b1 && i2 < i1)) { s1 = fmaxf(b1, s2); b1 = b2; i1 = i2; }
+  auto merge = [&beats](float& b1, int& i1, float& s1, float b2, int i2, float s2) {
+    if (beats(b2, i2, b1, i1)) { s1 = fmaxf(b1, s2); b1 = b2; i1 = i2; }
     else { s1 = fmaxf(s1, b2); }
   };
 #pragma unroll
@@ -92,7 +99,7 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int k = 1; k < (blockDim.x >> 5); ++k) merge(best, bi, second, sb[k], si[k], ss[k]);
-    out_idx[r] = bi;
+    out_idx[r] = (bi >= 0 && bi < cols) ? bi : 0;
     if (out_margin) out_margin[r] = best - second;
   }
 }
@@ -210,7 +217,8 @@ __device__ double clopper_pearson_lower(long long nA, long long n, double alpha,
 __global__ void __launch_bounds__(256) certify_tail_kernel(const long long* __restrict__ counts_sel,
                                                            const long long* __restrict__ counts_est,
                                                            int num_classes, long long n, double alpha,
-                                                           double sigma, int* __restrict__ out_label,
+                                                           double sigma, const double* __restrict__ lut,
+                                                           int* __restrict__ out_label,
                                                            double* __restrict__ out_stats) {
   __shared__ double sh[8];
   __shared__ long long s_best[256];
@@ -235,14 +243,18 @@ __global__ void __launch_bounds__(256) certify_tail_kernel(const long long* __re
   }
   const int cA = s_idx[0];
   const long long nA = counts_est[cA];
-  const double pABar = clopper_pearson_lower(nA, n, alpha, sh);
+  // lut (optional): [pABar(nA) | Phi^-1(pABar(nA))] for nA = 0..n, tabulated on the host once per (n, alpha) with the
+  // SciPy calls the reference makes per image (smoothing.py:55,117) -> pABar and radius bit-identical to the
+  // reference (the single fp64 multiply by sigma is IEEE-exact on both sides).  Without it: device bisection + AS241.
+  const bool use_lut = lut != nullptr && nA >= 0 && nA <= n;
+  const double pABar = use_lut ? lut[nA] : clopper_pearson_lower(nA, n, alpha, sh);
   if (threadIdx.x == 0) {
     if (pABar < 0.5) {
       out_label[0] = -1;
       out_stats[0] = 0.0;
     } else {
       out_label[0] = cA;
-      out_stats[0] = sigma * ppnd16(pABar);
+      out_stats[0] = __dmul_rn(sigma, use_lut ? lut[n + 1 + nA] : ppnd16(pABar));
     }
     out_label[1] = cA;
     out_stats[1] = pABar;
@@ -346,10 +358,11 @@ int label_hist(const int* labels, int B, int num_classes, long long* counts, int
 }
 
 int certify_tail(const long long* counts_sel, const long long* counts_est, int num_classes, long long n,
-                 double alpha, double sigma, int* out_label, double* out_stats, cudaStream_t stream) {
+                 double alpha, double sigma, const double* lut, int* out_label, double* out_stats,
+                 cudaStream_t stream) {
   CGPT_REQUIRE(num_classes > 0 && n > 0 && alpha > 0.0 && alpha < 1.0,
                "certify_tail: bad arguments classes=%d n=%lld alpha=%g", num_classes, n, alpha);
-  certify_tail_kernel<<<1, 256, 0, stream>>>(counts_sel, counts_est, num_classes, n, alpha, sigma,
+  certify_tail_kernel<<<1, 256, 0, stream>>>(counts_sel, counts_est, num_classes, n, alpha, sigma, lut,
                                              out_label, out_stats);
   CGPT_CHECK_CUDA(cudaGetLastError());
   count_launch();

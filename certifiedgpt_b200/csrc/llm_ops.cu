@@ -87,10 +87,14 @@ template <bool OUT_F32>
 __global__ void __launch_bounds__(128) gather_rows_kernel(const __nv_bfloat16* __restrict__ table, long long ldt,
                                                           const int* __restrict__ ids, int id_period, int D,
                                                           void* __restrict__ out, long long ldo,
-                                                          int remap_period, int remap_stride, int remap_offset) {
+                                                          int remap_period, int remap_stride, int remap_offset,
+                                                          int table_rows) {
   const int r = blockIdx.x;
   const int sel = r % id_period;
-  const long long src_row = ids ? ids[sel] : sel;
+  long long src_row = ids ? ids[sel] : sel;
+  // table_rows > 0: ids outside the table read row 0 instead of a wild address (an id can only leave the table
+  // through a poisoned upstream value, e.g. an all-NaN logits row; the caller validates user-supplied ids)
+  if (table_rows > 0 && (src_row < 0 || src_row >= table_rows)) src_row = 0;
   long long orow = r;
   if (remap_period > 0)
     orow = static_cast<long long>(r / remap_period) * remap_stride + remap_offset + (r % remap_period);
@@ -108,16 +112,18 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const __nv_bfloat16* _
 }
 
 int gather_rows(const void* table, long long ldt, const int* ids, int id_period, int rows, int D, void* out,
-                long long ldo, int out_dtype, int remap_period, int remap_stride, int remap_offset,
+                long long ldo, int out_dtype, int remap_period, int remap_stride, int remap_offset, int table_rows,
                 cudaStream_t stream) {
   CGPT_REQUIRE(rows > 0 && D > 0 && D % 8 == 0 && id_period > 0, "gather_rows: bad sizes rows=%d D=%d", rows, D);
+  CGPT_REQUIRE(ids != nullptr || table_rows <= 0 || id_period <= table_rows,
+               "gather_rows: id_period %d exceeds the table's %d rows", id_period, table_rows);
   CGPT_REQUIRE(ldt % 8 == 0 && ldo % 8 == 0, "gather_rows: leading dims must be multiples of 8");
   if (out_dtype == CGPT_DT_F32)
     gather_rows_kernel<true><<<rows, 128, 0, stream>>>((const __nv_bfloat16*)table, ldt, ids, id_period, D, out,
-                                                       ldo, remap_period, remap_stride, remap_offset);
+                                                       ldo, remap_period, remap_stride, remap_offset, table_rows);
   else
     gather_rows_kernel<false><<<rows, 128, 0, stream>>>((const __nv_bfloat16*)table, ldt, ids, id_period, D, out,
-                                                        ldo, remap_period, remap_stride, remap_offset);
+                                                        ldo, remap_period, remap_stride, remap_offset, table_rows);
   CGPT_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -33,7 +33,8 @@ int greedy_step(const int* next_idx, int B, int* finished, int* ids_out, int ld,
 int label_hist(const int* labels, int B, int num_classes, long long* counts, int* invalid,
                cudaStream_t stream);
 int certify_tail(const long long* counts_sel, const long long* counts_est, int num_classes, long long n,
-                 double alpha, double sigma, int* out_label, double* out_stats, cudaStream_t stream);
+                 double alpha, double sigma, const double* lut, int* out_label, double* out_stats,
+                 cudaStream_t stream);
 int predict_tail(const long long* counts, int num_classes, double alpha, int* out_label,
                  double* out_stats, cudaStream_t stream);
 int ce_loss(const float* logits, long long ld, int rows, int cols, const int* targets, float* token_loss,
@@ -52,7 +53,7 @@ int rope_split(void* qkv, long long ld, int rows, int T, int H, int head_dim, in
                const float* sin_t, void* kcache, void* vcache, long long ldc, int cache_rows_per_batch,
                int cache_row0, cudaStream_t stream);
 int gather_rows(const void* table, long long ldt, const int* ids, int id_period, int rows, int D, void* out,
-                long long ldo, int out_dtype, int remap_period, int remap_stride, int remap_offset,
+                long long ldo, int out_dtype, int remap_period, int remap_stride, int remap_offset, int table_rows,
                 cudaStream_t stream);
 // fine-tune step (train_ops.cu)
 int swiglu_fwd(const void* gu, void* act, long long rows, int inter, cudaStream_t s);

@@ -66,6 +66,7 @@ def _declare(lib):
         "cgpt_certify": [vp, vp, pns, i64, i64, f64, i32, i32, i32, vp, C.POINTER(i32), C.POINTER(f64),
                          C.POINTER(f64), vp],
         "cgpt_predict": [vp, vp, pns, i64, f64, i32, i32, i32, vp, C.POINTER(i32), C.POINTER(f64), vp],
+        "cgpt_set_radius_lut": [vp, i64, f64, vp],
         "cgpt_last_counts": [vp, C.POINTER(vp)],
         "cgpt_last_decode_steps": [vp],
         "cgpt_set_option": [vp, C.c_char_p, i32],
@@ -317,13 +318,16 @@ class NativeMiniGPT4Engine:
     @torch.no_grad()
     def certify(self, x, n0, n, alpha, batch_size, sigma, *, eps=None, seed=0, stream_id=0,
                 noise_space=L.SPACE_NORMALIZED, noise_kind=L.NOISE_GAUSSIAN, mean=L.BLIP_MEAN, std=L.BLIP_STD,
-                process_group=None):
+                process_group=None, exact_tail=True):
         """Smooth.certify in one library call.  x: [3,S,S] fp32, host (pinned or pageable) or device.
         Returns (label or -1, radius, detail dict)."""
         self._check_x(x)
         self.reserve(min(int(batch_size), int(n0 + n)))
         rank, world, comm = self._comm_for(process_group)
         spec = self._spec(sigma, seed, stream_id, noise_space, noise_kind, mean, std, eps, 0)
+        # pABar / radius table of this (n, alpha), built once on the host with the reference's SciPy calls
+        self._lut = L.radius_lut(n, alpha, self.dev) if exact_tail else None
+        L.check(self._lib.cgpt_set_radius_lut(self._h, int(n), float(alpha), L.ptr(self._lut)))
         label, radius = C.c_int(0), C.c_double(0.0)
         detail = (C.c_double * 3)()
         with torch.cuda.device(self.dev):

@@ -9,7 +9,8 @@ Monte-Carlo loop runs on the device through libcgpt.so (include/cgpt.h):
   base_classifier(batch).argmax(1)                     fused MiniGPT-4 engine, or any nn.Module
   predictions.cpu().numpy()  (sync per batch)          labels stay on the device
   _count_arr Python loop                               warp-aggregated histogram kernel
-  scipy/statsmodels tail on the host                   fp64 device tail kernel, ONE D2H read
+  scipy/statsmodels tail on the host                   device tail kernel over a per-(n, alpha) SciPy table
+                                                       (bit-identical radius), ONE D2H read
 
 Extras (keyword-only, all optional): `seed`, `noise_space`, `noise_kind`, `process_group`
 (shards the N draws across ranks; one int64 all-reduce per _sample_noise) and
@@ -37,7 +38,8 @@ class Smooth(object):
 
     def __init__(self, base_classifier, num_classes: int, sigma: float, *, seed: int = 0,
                  noise_space: str = "normalized", noise_kind: str = "gaussian",
-                 mean=L.BLIP_MEAN, std=L.BLIP_STD, process_group=None, fuse_selection: bool = True):
+                 mean=L.BLIP_MEAN, std=L.BLIP_STD, process_group=None, fuse_selection: bool = True,
+                 exact_tail: bool = True):
         """
         :param base_classifier: maps [batch x channel x height x width] to [batch x num_classes]
                (any torch.nn.Module), or a fused engine exposing `noisy_labels(...)`
@@ -53,6 +55,10 @@ class Smooth(object):
         self.mean, self.std = tuple(mean), tuple(std)
         self.process_group = process_group
         self.fuse_selection = fuse_selection
+        # True: pABar and Phi^-1 come from a per-(n, alpha) table built once on the host by the SciPy calls the
+        # reference makes per image (smoothing.py:55,117) -> (label, radius) bit-identical to the reference;
+        # False: fp64 device bisection + AS241 (1e-12 relative), no SciPy anywhere
+        self.exact_tail = exact_tail
         self.image_id = 0          # Philox stream id; bumped per certify/predict call
         self._cursor = 0           # global sample index inside the current call
         self._injected = None
@@ -76,7 +82,7 @@ class Smooth(object):
             # x may live on the host (the library stages it) or on the device
             label, radius, d = self.base_classifier.certify(
                 self._as_f32(x), n0, n, alpha, batch_size, self.sigma, eps=self._injected, process_group=self.process_group,
-                **self._noise_kw())
+                exact_tail=self.exact_tail, **self._noise_kw())
             self.last_cAHat, self.last_pABar = d["cAHat"], d["pABar"]
             self.last_counts_selection, self.last_counts_estimation = d["counts_selection"], d["counts_estimation"]
             self.last_counts = self.last_counts_selection
@@ -90,7 +96,8 @@ class Smooth(object):
         else:
             counts_selection = self._sample_noise_device(x, n0, batch_size)
             counts_estimation = self._sample_noise_device(x, n, batch_size)
-        lab, st = L.certify_tail(counts_selection, counts_estimation, n, alpha, self.sigma)
+        lut = L.radius_lut(n, alpha, counts_estimation.device) if self.exact_tail else None
+        lab, st = L.certify_tail(counts_selection, counts_estimation, n, alpha, self.sigma, lut)
         label = int(lab[0].item())         # the one device->host read of the call
         radius = float(st[0].item())
         self.last_cAHat = int(lab[1].item())
@@ -135,7 +142,7 @@ class Smooth(object):
         dev = torch.device("cuda", torch.cuda.current_device())
         sel = torch.ones(1, dtype=torch.int64, device=dev)
         est = torch.full((1,), int(NA), dtype=torch.int64, device=dev)
-        _, st = L.certify_tail(sel, est, N, alpha, 1.0)
+        _, st = L.certify_tail(sel, est, N, alpha, 1.0, L.radius_lut(N, alpha, dev) if self.exact_tail else None)
         return float(st[1].item())
 
     # ------------------------------------------------------------------ device loop

@@ -91,6 +91,30 @@ def random_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32, parts=("vi
     return sd
 
 
+def aliased_state_dict(cfg, seed=0, round_bf16=False):
+    """Full-depth state dict whose transformer layers ALIAS the tensors of the first layer of each tower (Q-Former: the
+    first cross and the first plain layer): identical shapes, FLOPs and bytes per layer at a fraction of the host RAM
+    and init time of 7 B distinct parameters.  For host-side work at BASELINE.json's full shape: the CPU timing sample
+    of bench.py and the full-shape parity test, where the fp32 oracle and the engine must hold the SAME weights."""
+    import copy
+    c1 = copy.deepcopy(cfg)
+    c1.vit.depth, c1.qf.layers, c1.llm.layers = 1, min(cfg.qf.layers, 2), 1
+    sd = random_state_dict(c1, seed=seed)
+    if round_bf16:
+        sd = round_to_bf16(sd)
+    for i in range(1, cfg.vit.depth):
+        for k in [k for k in sd if k.startswith("visual_encoder.blocks.0.")]:
+            sd[k.replace("blocks.0.", f"blocks.{i}.")] = sd[k]
+    for i in range(2, cfg.qf.layers):
+        src = i % 2
+        for k in [k for k in sd if k.startswith(f"Qformer.bert.encoder.layer.{src}.")]:
+            sd[k.replace(f"layer.{src}.", f"layer.{i}.")] = sd[k]
+    for i in range(1, cfg.llm.layers):
+        for k in [k for k in sd if k.startswith("llama_model.model.layers.0.")]:
+            sd[k.replace("layers.0.", f"layers.{i}.")] = sd[k]
+    return sd
+
+
 def round_to_bf16(sd):
     """The same state dict with every GEMM weight rounded to bf16 (kept as fp32 tensors): the
     oracle then multiplies exactly the weights the GPU holds, so differences are activation

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CGPT_ABI_VERSION 2
+#define CGPT_ABI_VERSION 3
 
 enum { CGPT_DT_BF16 = 0, CGPT_DT_F32 = 1 };
 enum { CGPT_ACT_NONE = 0, CGPT_ACT_GELU = 1, CGPT_ACT_SWIGLU = 2, CGPT_ACT_QUICKGELU = 3 /* x*sigmoid(1.702x), CLIP */ };
@@ -133,6 +133,14 @@ int cgpt_label_hist(const int32_t* labels, int B, int num_classes, int64_t* coun
 int cgpt_certify_tail(const int64_t* counts_sel, const int64_t* counts_est, int num_classes,
                       int64_t n, double alpha, double sigma, int32_t* out_label,
                       double* out_stats, void* stream);
+/* The same tail with pABar and Phi^-1(pABar) read from a caller-built table instead of the device bisection:
+ * lut = device double[2 * (n + 1)], lut[nA] = _lower_confidence_bound(nA, n, alpha) and lut[n + 1 + nA] =
+ * norm.ppf(lut[nA]) for nA = 0..n, tabulated on the host once per (n, alpha) with the very calls the reference makes
+ * per image (smoothing.py:55,117: scipy.stats.beta.ppf / norm.ppf).  (label, pABar, radius) are then BIT-IDENTICAL to
+ * the reference: the only device arithmetic left is the IEEE fp64 product sigma * lut[n + 1 + nA]. */
+int cgpt_certify_tail_lut(const int64_t* counts_sel, const int64_t* counts_est, int num_classes,
+                          int64_t n, double alpha, double sigma, const double* lut, int32_t* out_label,
+                          double* out_stats, void* stream);
 /* smoothing.py:73-79.  out_label[0] = class or -1, [1],[2] = top-2 classes;
  * out_stats[0] = p-value, [1],[2] = top-2 counts */
 int cgpt_predict_tail(const int64_t* counts, int num_classes, double alpha, int32_t* out_label,
@@ -193,10 +201,11 @@ int cgpt_rope_split(void* qkv, int64_t ld, int rows, int T, int H, int head_dim,
                     const float* cos_table, const float* sin_table, void* kcache, void* vcache,
                     int64_t ld_cache, int cache_rows_per_batch, int cache_row0, void* stream);
 /* out[remap(r)] = table[ids ? ids[r % id_period] : r % id_period]  (embed_tokens gather and
- * row broadcast: minigpt_base.py:75-89,367-372,399-412; query_tokens.expand minigpt4.py:133) */
+ * row broadcast: minigpt_base.py:75-89,367-372,399-412; query_tokens.expand minigpt4.py:133).
+ * table_rows > 0: ids outside [0, table_rows) read row 0 instead of an address outside the table. */
 int cgpt_gather_rows(const void* table, int64_t ldt, const int32_t* ids, int id_period, int rows, int D,
                      void* out, int64_t ldo, int out_dtype, int remap_period, int remap_stride,
-                     int remap_offset, void* stream);
+                     int remap_offset, int table_rows, void* stream);
 
 
 /* ---------------------------------------------------------------- GEMM timing hook (bench.py roofline)
@@ -336,6 +345,10 @@ int cgpt_sample_noise(cgpt_handle h, const float* x, const cgpt_noise_spec* nois
 int cgpt_certify(cgpt_handle h, const float* x, const cgpt_noise_spec* noise, int64_t n0, int64_t n, double alpha,
                  int batch_size, int rank, int world, void* comm, int* out_label, double* out_radius,
                  double* out_detail, void* stream);
+/* Bind the (n, alpha) table of cgpt_certify_tail_lut to the handle (caller-owned device memory, like the weights;
+ * NULL unbinds): cgpt_certify calls with exactly this n and alpha take pABar / radius from it (bit-identical to the
+ * reference's SciPy tail), every other call uses the device bisection. */
+int cgpt_set_radius_lut(cgpt_handle h, int64_t n, double alpha, const double* lut);
 /* Smooth.predict (smoothing.py:58-79); out_detail (host, nullable) double[1] = {p-value} */
 int cgpt_predict(cgpt_handle h, const float* x, const cgpt_noise_spec* noise, int64_t n, double alpha,
                  int batch_size, int rank, int world, void* comm, int* out_label, double* out_detail,

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in _declared_symbols() if not hasattr(lib, n)]
     assert not missing, f"libcgpt.so lacks {missing}"
     lib.cgpt_abi_version.restype = ctypes.c_int
-    assert lib.cgpt_abi_version() == 2
+    assert lib.cgpt_abi_version() == 3
 
 
 def test_no_cpu_fallback_for_compute():

@@ -106,26 +106,31 @@ def test_smooth_certify_with_engine_matches_oracle(space):
         x = (x - m) / s
     n0, n, sigma, alpha = 40, 200, 0.25, 0.001
     eps = torch.randn(n0 + n, 3, S, S, generator=torch.Generator().manual_seed(1234))
-    cur = {"base": 0}
-    oracle = so.SmoothOracle(orc, 6, sigma, noise_fn=lambda d, c, b: eps[cur["base"] + d: cur["base"] + d + c])
-    sel = oracle._sample_noise(x, n0, 64)
-    m_sel = orc.last["margins"]
-    cur["base"] = n0
-    est = oracle._sample_noise(x, n, 64)
-    ref_label, ref_radius = so.certify_tail(sel, est, n, alpha, sigma)
-
     ours = Smooth(eng, 6, sigma, noise_space=space)
     ours.inject_noise(eps.cuda())
     label, radius = ours.certify(x.cuda(), n0, n, alpha, 64)
-    got_sel = ours.last_counts_selection.cpu().numpy()
-    got_est = ours.last_counts_estimation.cpu().numpy()
-    assert got_sel.sum() == n0 and got_est.sum() == n
-    # counts may differ only by samples whose oracle margin is below the threshold
-    # (collect all margins by re-running the oracle per batch is costly; bound the L1 distance instead)
-    assert np.abs(got_sel - sel).sum() <= 2 * max(1, int(0.05 * n0))
-    assert np.abs(got_est - est).sum() <= 2 * max(1, int(0.05 * n))
-    if np.array_equal(got_sel, sel) and np.array_equal(got_est, est):
-        assert label == ref_label and radius == pytest.approx(ref_radius, rel=1e-9)
+    got_sel = ours.last_counts_selection.cpu()
+    got_est = ours.last_counts_estimation.cpu()
+    assert int(got_sel.sum()) == n0 and int(got_est.sum()) == n
+    # per sample: the engine's label of every draw equals the oracle's wherever the oracle's top-2 margin is safe
+    kw = dict(noise_space=L.SPACE_PIXEL, mean=L.BLIP_MEAN, std=L.BLIP_STD) if space == "pixel" else {}
+    lab = torch.cat([eng.noisy_labels(x.cuda(), min(50, n0 + n - f), sigma, eps=eps[f:f + 50].cuda(), first_sample=f, **kw)
+                     for f in range(0, n0 + n, 50)]).cpu().long()
+    assert torch.equal(torch.bincount(lab[:n0], minlength=6), got_sel)      # counts = histogram of per-sample labels
+    assert torch.equal(torch.bincount(lab[n0:], minlength=6), got_est)
+    ref, margins = [], []
+    for f in range(0, n0 + n, 60):
+        orc(x[None] + eps[f:f + 60] * sigma)
+        ref.append(orc.last["labels"].clone())
+        margins.append(orc.last["margins"].clone())
+    ref, safe = torch.cat(ref), (torch.cat(margins) > MARGIN).all(dim=1)
+    assert safe.float().mean() > 0.5
+    assert torch.equal(lab[safe], ref[safe])
+    ref_sel, ref_est = torch.bincount(ref[:n0], minlength=6), torch.bincount(ref[n0:], minlength=6)
+    assert int((got_sel - ref_sel).abs().sum()) <= 2 * int((~safe[:n0]).sum())
+    assert int((got_est - ref_est).abs().sum()) <= 2 * int((~safe[n0:]).sum())
+    if torch.equal(got_sel, ref_sel) and torch.equal(got_est, ref_est):
+        assert (label, radius) == so.certify_tail(ref_sel.numpy(), ref_est.numpy(), n, alpha, sigma)
 
 
 def test_noisy_labels_per_sample_match_oracle_where_margin_safe():

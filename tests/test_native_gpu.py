@@ -106,6 +106,7 @@ def test_smooth_native_matches_oracle_on_injected_noise(use_graphs):
     sm = Smooth(nat, n_classes, sigma)
     sm.inject_noise(eps.cuda())
     label, radius = sm.certify(x.cuda(), n0, n, alpha, 32)
+    sm.last_label, sm.last_radius = label, radius
     got_sel, got_est = sm.last_counts_selection.cpu().numpy(), sm.last_counts_estimation.cpu().numpy()
     # the Python twin on the same injected noise: identical counts, label, radius
     sp = Smooth(py, n_classes, sigma)
@@ -114,18 +115,56 @@ def test_smooth_native_matches_oracle_on_injected_noise(use_graphs):
     assert np.array_equal(got_sel, sp.last_counts_selection.cpu().numpy())
     assert np.array_equal(got_est, sp.last_counts_estimation.cpu().numpy())
     assert (label, radius) == (plabel, pradius)
-    # the oracle: counts may differ only where its top-2 margin is below 1e-2
-    cur = {"base": 0}
-    oracle = so.SmoothOracle(orc, n_classes, sigma, noise_fn=lambda d, c, b: eps[cur["base"] + d: cur["base"] + d + c])
-    sel = oracle._sample_noise(x, n0, 32)
-    cur["base"] = n0
-    est = oracle._sample_noise(x, n, 32)
-    assert got_sel.sum() == n0 and got_est.sum() == n
-    unsafe = int((np.array(oracle.last_margins) <= MARGIN).sum()) if hasattr(oracle, "last_margins") else 8
-    assert np.abs(got_sel - sel).sum() + np.abs(got_est - est).sum() <= 2 * max(unsafe, 4)
-    if np.array_equal(got_sel, sel) and np.array_equal(got_est, est):
-        ref = so.certify_tail(sel, est, n, alpha, sigma)
-        assert label == ref[0] and abs(radius - ref[1]) <= 1e-9 * max(1.0, abs(ref[1]))
+    # the oracle, PER SAMPLE: every draw whose top-2 logit margin exceeds 1e-2 at every decode step gets the oracle's label,
+    # and the count vectors are exactly the histogram of the per-sample labels
+    _assert_per_sample_parity(nat, orc, sm, x, eps, n0, n, sigma, alpha, n_classes, bs=32)
+
+
+def _oracle_per_sample(orc, x, eps, sigma, bs=64):
+    labels, margins = [], []
+    for f in range(0, eps.shape[0], bs):
+        orc(x[None] + eps[f:f + bs] * sigma)
+        labels.append(orc.last["labels"].clone())
+        margins.append(orc.last["margins"].clone())
+    labels, margins = torch.cat(labels), torch.cat(margins)
+    return labels, (margins > MARGIN).all(dim=1)
+
+
+def _assert_per_sample_parity(nat, orc, sm, x, eps, n0, n, sigma, alpha, n_classes, bs):
+    """`sm` has just run certify(x, n0, n, alpha, bs) over `nat` on the injected draws `eps` [n0+n]."""
+    got_sel, got_est = sm.last_counts_selection.cpu(), sm.last_counts_estimation.cpu()
+    lab = torch.cat([nat.noisy_labels(x.cuda(), min(97, n0 + n - f), sigma, eps=eps[f:f + 97].cuda(), first_sample=f)
+                     for f in range(0, n0 + n, 97)]).cpu().long()          # another batching: labels are per-sample
+    assert torch.equal(torch.bincount(lab[:n0], minlength=n_classes), got_sel)
+    assert torch.equal(torch.bincount(lab[n0:], minlength=n_classes), got_est)
+    ref, safe = _oracle_per_sample(orc, x, eps, sigma)
+    assert safe.float().mean() > 0.5, "test inputs too close to ties to be informative"
+    assert torch.equal(lab[safe], ref[safe])                                # bit-exact wherever the margin is safe
+    # hence the counts differ from the oracle's by at most the unsafe draws, and not at all without them
+    ref_sel = torch.bincount(ref[:n0], minlength=n_classes)
+    ref_est = torch.bincount(ref[n0:], minlength=n_classes)
+    unsafe_sel, unsafe_est = int((~safe[:n0]).sum()), int((~safe[n0:]).sum())
+    assert int((got_sel - ref_sel).abs().sum()) <= 2 * unsafe_sel
+    assert int((got_est - ref_est).abs().sum()) <= 2 * unsafe_est
+    if torch.equal(got_sel, ref_sel) and torch.equal(got_est, ref_est):
+        want = so.certify_tail(ref_sel.numpy(), ref_est.numpy(), n, alpha, sigma)
+        assert (sm.last_label, sm.last_radius) == want                      # label and radius bit-exact
+
+
+def test_certify_n0_100_n_1000_per_sample_parity_on_the_wide_config():
+    """BASELINE configs[1]'s draw counts (N0 = 100, N = 1000) through cgpt_certify on the wide model: per-sample labels
+    equal the oracle's wherever its top-2 margin exceeds 1e-2 (north_star), counts are their histogram."""
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    cfg, n_classes = WIDE, 8
+    sd, py, nat, orc = _setup(cfg, seed=31, max_new=3, n_classes=n_classes, oracle=True)
+    S = cfg.vit.img_size
+    x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(1000))
+    n0, n, sigma, alpha = 100, 1000, 0.25, 0.001
+    eps = torch.randn(n0 + n, 3, S, S, generator=torch.Generator().manual_seed(1234))
+    sm = Smooth(nat, n_classes, sigma)
+    sm.inject_noise(eps.cuda())
+    sm.last_label, sm.last_radius = sm.certify(x.cuda(), n0, n, alpha, 256)
+    _assert_per_sample_parity(nat, orc, sm, x, eps, n0, n, sigma, alpha, n_classes, bs=256)
 
 
 def test_certify_predict_host_x_and_batch_size_invariance():

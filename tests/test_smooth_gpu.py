@@ -62,8 +62,15 @@ def test_certify_matches_oracle(sigma, seed):
     assert np.array_equal(ours.last_counts_selection.cpu().numpy(), sel)
     assert np.array_equal(ours.last_counts_estimation.cpu().numpy(), est)
     assert label == ref_label
-    assert radius == pytest.approx(ref_radius, rel=1e-9)
+    assert radius == ref_radius          # bit-exact: per-(n, alpha) SciPy table, IEEE fp64 product on the device
+    assert ours.last_pABar == so.lower_confidence_bound(int(est[ref_label if ref_label >= 0 else ours.last_cAHat]), n, 0.001)
     assert isinstance(label, int) and isinstance(radius, float)
+    # the table-free device tail (fp64 bisection + AS241) stays as the cross-check
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    dev = Smooth(ours.base_classifier, ours.num_classes, sigma, exact_tail=False)
+    dev.inject_noise(ours._injected)
+    l2, r2 = dev.certify(x.cuda(), n0, n, 0.001, 128)
+    assert l2 == label and r2 == pytest.approx(radius, rel=1e-9)
 
 
 def test_predict_matches_oracle():
@@ -91,7 +98,9 @@ def test_helpers_match_reference_semantics():
     from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
     s = Smooth(torch.nn.Identity(), 5, 0.25)
     assert s._count_arr(np.array([0, 4, 4, 2]), 5).tolist() == [1, 0, 1, 0, 2]
-    assert s._lower_confidence_bound(990, 1000, 0.001) == pytest.approx(0.9760361871553114, rel=1e-9)
+    assert s._lower_confidence_bound(990, 1000, 0.001) == 0.9760361871553114      # SURVEY 8c known answer, exact
+    assert Smooth(torch.nn.Identity(), 5, 0.25, exact_tail=False)._lower_confidence_bound(990, 1000, 0.001) == \
+        pytest.approx(0.9760361871553114, rel=1e-9)
     assert s._lower_confidence_bound(0, 1000, 0.001) == 0.0
     assert Smooth.ABSTAIN == -1
 
@@ -141,10 +150,19 @@ def test_cuda_smooth_equals_the_reference_smooth_run(case):
     label, radius = ours.certify(x.cuda(), n0, n, alpha, bs)
     assert ours.last_counts_selection.cpu().tolist() == case["counts_selection"]
     assert ours.last_counts_estimation.cpu().tolist() == case["counts_estimation"]
-    assert label == case["certify"][0] and radius == pytest.approx(case["certify"][1], rel=1e-9, abs=0)
+    assert label == case["certify"][0] and radius == case["certify"][1]       # bit-exact radius
+    assert ours.last_pABar == so.lower_confidence_bound(case["counts_estimation"][ours.last_cAHat], n, alpha)
     # the reference's two separate _sample_noise calls (no fused selection pass) give the same result
     seq = Smooth(model.cuda(), case["classes"], case["sigma"], fuse_selection=False)
     seq.inject_noise(eps.cuda())
     assert seq.certify(x.cuda(), n0, n, alpha, bs) == (label, radius)
     assert ours.predict(x.cuda(), n, alpha, bs) == case["predict"]
     assert ours.last_counts.cpu().tolist() == case["predict_counts"]
+
+
+def test_lower_confidence_bound_equals_the_reference_run_exactly():
+    """Smooth._lower_confidence_bound against the values the reference's own smoothing.py produced: equal bit for bit."""
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    s = Smooth(torch.nn.Identity(), 5, 0.25)
+    for row in REF_SMOOTH["lower_confidence_bound"]:
+        assert s._lower_confidence_bound(row["NA"], row["N"], row["alpha"]) == row["value"], row
