@@ -40,6 +40,7 @@ class GemmEpilogue(C.Structure):
         ("remap_stride", C.c_int), ("remap_offset", C.c_int),
         ("max_ctas", C.c_int),
         ("rope", C.POINTER(GemmRope)),
+        ("hm_T", C.c_int), ("hm_heads", C.c_int), ("hm_hd", C.c_int),
     ]
 
 
@@ -51,7 +52,7 @@ class AttnArgs(C.Structure):
         ("kp", C.c_void_p), ("vp", C.c_void_p), ("ldkp", C.c_int64), ("ldvp", C.c_int64), ("P", C.c_int),
         ("o", C.c_void_p), ("ldo", C.c_int64),
         ("B", C.c_int), ("H", C.c_int), ("Tq", C.c_int), ("Tk", C.c_int), ("head_dim", C.c_int),
-        ("scale", C.c_float), ("causal", C.c_int), ("decode_kernel", C.c_int),
+        ("scale", C.c_float), ("causal", C.c_int), ("decode_kernel", C.c_int), ("head_major", C.c_int),
     ]
 
 
@@ -175,8 +176,9 @@ def gemm_profile_stop():
 
 def gemm(a, w, *, out=None, bias=None, resid=None, act=ACT_NONE, out_dtype=torch.bfloat16,
          row_add=None, row_period=0, row_add_offset=0, remap_stride=0, remap_offset=0,
-         out_rows=None, force_bn=0, max_ctas=0, rope=None):
-    """out = epilogue(a @ w.T); a [M,K] bf16 (row stride may exceed K), w [N,K] bf16."""
+         out_rows=None, force_bn=0, max_ctas=0, rope=None, headmajor=None):
+    """out = epilogue(a @ w.T); a [M,K] bf16 (row stride may exceed K), w [N,K] bf16.
+    headmajor=(T, heads, hd): fused q|k|v projection scattered as [3][M/T][heads][T][hd] into `out` (same bytes)."""
     lib = load()
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.stride(1) == 1 and w.stride(1) == 1
@@ -212,6 +214,9 @@ def gemm(a, w, *, out=None, bias=None, resid=None, act=ACT_NONE, out_dtype=torch
         r.ld_cache = rope["kcache"].stride(-2)
         r.cache_rows_per_batch, r.cache_row0 = rope["cache_rows"], rope["cache_row0"]
         e.rope = C.pointer(r)
+    if headmajor is not None:
+        e.hm_T, e.hm_heads, e.hm_hd = (int(v) for v in headmajor)
+        assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.numel() >= M * N
     check(lib.cgpt_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K,
                              C.byref(e), force_bn, stream_ptr()))
     return out
@@ -416,11 +421,23 @@ def norm_rows(x, gamma, beta, eps, out, *, rms=False, rows=None, gather=None):
     return out
 
 
+def attn_vit_supported(*, B, H, T, head_dim):
+    """True when the pipelined head-major tcgen05 attention kernel (csrc/attn_vit.cu) serves this non-causal shape."""
+    E = 1 if T > 256 else 0
+    return (64 < head_dim <= (96 if E else 128) and head_dim % 8 == 0 and 1 <= T - E <= 256
+            and B * H * T < 2 ** 31)
+
+
 def attention(q, k, v, o, *, B, H, Tq, Tk, head_dim, scale, q_rows_per_batch=None,
-              kv_rows_per_batch=None, causal=False, kp=None, vp=None, P=0, decode=False, force_flash=False):
-    """q/k/v/o are 2-D bf16 views whose column 0 is head 0 (e.g. slices of a fused QKV buffer)."""
+              kv_rows_per_batch=None, causal=False, kp=None, vp=None, P=0, decode=False, force_flash=False,
+              head_major=False):
+    """q/k/v/o are 2-D bf16 views whose column 0 is head 0 (e.g. slices of a fused QKV buffer).
+    head_major=True: q, k, v are dense [B][H][T][head_dim] blocks (gemm(..., headmajor=...))."""
     lib = load()
     a = AttnArgs()
+    a.head_major = 1 if head_major else 0
+    if head_major:
+        assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous() and Tq == Tk
     a.q = q.data_ptr(); a.ldq = q.stride(0); a.q_rows_per_batch = q_rows_per_batch or Tq
     a.k = k.data_ptr(); a.v = v.data_ptr(); a.ldk = k.stride(0); a.ldv = v.stride(0)
     a.kv_rows_per_batch = kv_rows_per_batch or (Tk - P)

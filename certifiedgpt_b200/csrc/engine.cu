@@ -198,6 +198,7 @@ struct Epi {
   Epi& row_add(const float* p, long long ld, int offset) { e.row_add = p; e.ld_row_add = ld; e.row_add_offset = offset; return *this; }
   Epi& rope(const cgpt_gemm_rope* r) { e.rope = r; return *this; }
   Epi& remap(int period, int stride, int offset) { e.row_period = period; e.remap_stride = stride; e.remap_offset = offset; return *this; }
+  Epi& headmajor(int T, int heads, int hd) { e.hm_T = T; e.hm_heads = heads; e.hm_hd = hd; return *this; }
 };
 inline int gemm(const void* A, long long lda, const void* W, int M, int N, int K, const Epi& epi, cudaStream_t s) {
   return gemm_bf16(A, lda, W, K, M, N, K, &epi.e, 0, s);
@@ -409,12 +410,28 @@ int vit_forward(Engine* E, const void* patches, int B, void* out, cudaStream_t s
                 Epi(res, D, CGPT_DT_F32).bias(E->patch_b).row_add(E->pos, D, 1).remap(Pn, T, 1), s));
   CGPT_TRY(set_rows_f32(res, static_cast<long long>(T) * D, E->cls_pos, D, B, s));
   const float scale = 1.0f / sqrtf(static_cast<float>(E->vhd));
+  // head-major q / k / v ([3][B][H][T][hd], written by the QKV GEMM's scatter epilogue) + the pipelined tcgen05
+  // attention kernel whenever the shape allows (224 px: T = 257); row-major + the generic dispatcher otherwise (448 px)
+  cgpt_attn_args hm;
+  memset(&hm, 0, sizeof(hm));
+  const long long MD = static_cast<long long>(M) * D;
+  hm.q = b.v_qkv; hm.k = bf(b.v_qkv) + MD; hm.v = bf(b.v_qkv) + 2 * MD;
+  hm.q_rows_per_batch = T; hm.kv_rows_per_batch = T; hm.o = b.v_att; hm.ldo = D;
+  hm.B = B; hm.H = c.vit_heads; hm.Tq = T; hm.Tk = T; hm.head_dim = E->vhd; hm.scale = scale; hm.head_major = 1;
+  static const bool no_hm = getenv("CGPT_VIT_ROW_MAJOR") != nullptr;   // A/B switch: the round-1 layout and kernel
+  const bool use_hm = !no_hm && attn_vit_supported(&hm);
   for (int i = 0; i < c.vit_depth; ++i) {
     const VitLayer& L = E->vit[i];
     CGPT_TRY(norm_rows(res, D, CGPT_DT_F32, L.ln1w, L.ln1b, c.vit_eps, M, D, b.v_xn, D, CGPT_DT_BF16, 0, 0, 0, 0, s));
-    CGPT_TRY(gemm(b.v_xn, D, L.qkvw, M, 3 * D, D, Epi(b.v_qkv, 3 * D, CGPT_DT_BF16).bias(L.qkvb), s));
-    CGPT_TRY(attn(b.v_qkv, 3 * D, T, bf(b.v_qkv) + D, bf(b.v_qkv) + 2 * D, 3 * D, T, b.v_att, D, B, c.vit_heads, T, T,
-                  E->vhd, scale, 0, 0, s));
+    if (use_hm) {
+      CGPT_TRY(gemm(b.v_xn, D, L.qkvw, M, 3 * D, D,
+                    Epi(b.v_qkv, 3 * D, CGPT_DT_BF16).bias(L.qkvb).headmajor(T, c.vit_heads, E->vhd), s));
+      CGPT_TRY(attention(&hm, s));
+    } else {
+      CGPT_TRY(gemm(b.v_xn, D, L.qkvw, M, 3 * D, D, Epi(b.v_qkv, 3 * D, CGPT_DT_BF16).bias(L.qkvb), s));
+      CGPT_TRY(attn(b.v_qkv, 3 * D, T, bf(b.v_qkv) + D, bf(b.v_qkv) + 2 * D, 3 * D, T, b.v_att, D, B, c.vit_heads, T, T,
+                    E->vhd, scale, 0, 0, s));
+    }
     CGPT_TRY(gemm(b.v_att, D, L.projw, M, D, D,
                   Epi(res, D, CGPT_DT_F32).bias(L.projb).resid(res, D, CGPT_DT_F32), s));
     CGPT_TRY(norm_rows(res, D, CGPT_DT_F32, L.ln2w, L.ln2b, c.vit_eps, M, D, b.v_xn, D, CGPT_DT_BF16, 0, 0, 0, 0, s));

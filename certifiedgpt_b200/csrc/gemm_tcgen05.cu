@@ -75,6 +75,11 @@ struct EpiParams {
   const float* rope_cos; const float* rope_sin; // [max_pos, 64]
   __nv_bfloat16* rope_k; __nv_bfloat16* rope_v; // KV cache
   long long rope_ldc; int rope_cache_rows, rope_cache_row0;
+  // head-major scatter of a fused q|k|v projection (cgpt_gemm_epilogue.hm_*): out_row carries the (sample, token) part
+  // of the address, the column part is worked out per 8-element piece (warp-uniform)
+  int hm_T, hm_H, hm_hd, hm_D;                  // rows per sample, heads, head dim, H * hd
+  float hm_inv_hd;
+  long long hm_ws;                              // elements between the q, k and v blocks = M * D
   long long* dbg;     // optional per-CTA cycle counters (CGPT_GEMM_DBG): [grid][8]
 };
 
@@ -184,6 +189,23 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
 #pragma unroll
     for (int i = 0; i < NC; ++i) v[i] += resid_r[i];
   }
+  if (p.hm_T > 0) {
+    // 8-element pieces never straddle a head (hd % 8 == 0); which / h / d are the same for the whole warp
+#pragma unroll
+    for (int i = 0; i < NC; i += 8) {
+      const int n = n0 + i;
+      const int which = (n >= p.hm_D) + (n >= 2 * p.hm_D);
+      const int rem = n - which * p.hm_D;
+      const int h = static_cast<int>((static_cast<float>(rem) + 0.5f) * p.hm_inv_hd);
+      const int d = rem - h * p.hm_hd;
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + which * p.hm_ws + out_row +
+                         static_cast<long long>(h) * p.hm_T * p.hm_hd + d;
+      __stcs(reinterpret_cast<uint4*>(o),
+             make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                        pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7])));
+    }
+    return;
+  }
   if (p.out_f32) {
     float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
 #pragma unroll
@@ -239,19 +261,44 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams&
 // of MMA).  Instead each warp transposes its [32 rows x 16 cols] chunk through a private shared-memory patch so that
 // 4 adjacent lanes cover 64 contiguous bytes of one row: 8 rows x 2 full sectors per instruction, 4x fewer L2
 // requests.  Same single fp32 addition per element as before (every element is still touched by exactly one thread).
+// RMW = true replaces the reduction by a plain load + add + store in that transposed domain: the per-SM issue rate of
+// RED (~1.3 cycles per lane and request, B300_MICROARCH "Atomics") made 8192 requests per 128 x 256 tile cost ~10.6k
+// cycles against 11.3k cycles of MMA for K = 1408, while 256 coalesced 16-byte loads + 256 stores cost ~2k.
+template <bool RMW>
 __device__ __forceinline__ void epilogue_chunks_red(uint32_t t_row, const EpiParams& p, const float* bias_s, float* stage,
                                                     int m_warp0, int M, int n_base, int N, int c0, int c1) {
   const int lane = threadIdx.x & 31;
   uint32_t r0[16], r1[16];
   const int srow = lane >> 2, scol = (lane & 3) * 4;        // this lane's (row within a group of 8, column) on the way out
+  // the 4 output rows this lane serves in every chunk (k * 8 + srow), fixed for the whole tile
+  float* orow[4];
+  bool rok[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int m = m_warp0 + k * 8 + srow;
+    rok[k] = m < M;
+    long long o = m;
+    if (p.row_period > 0 && p.remap_stride > 0)
+      o = (long long)(m / p.row_period) * p.remap_stride + p.remap_offset + (m % p.row_period);
+    orow[k] = reinterpret_cast<float*>(p.out) + o * p.ldo + scol;
+  }
   tmem_ld_x16(t_row + c0 * 16, r0);
 #pragma unroll 1
   for (int c = c0; c < c1; ++c) {
+    const int n0 = n_base + c * 16;
+    // RMW form: the residual values of this chunk are requested BEFORE the TMEM wait and the shared-memory transpose,
+    // so most of their L2 latency hides behind those steps (4 independent 16-byte loads per lane, 64 contiguous bytes
+    // per row and instruction)
+    float4 old[4];
+    if (RMW && n0 < N) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (rok[k]) old[k] = *reinterpret_cast<const float4*>(orow[k] + n0);
+    }
     tmem_ld_wait();
     uint32_t* cur = ((c - c0) & 1) ? r1 : r0;
     uint32_t* nxt = ((c - c0) & 1) ? r0 : r1;
     if (c + 1 < c1) tmem_ld_x16(t_row + (c + 1) * 16, nxt);
-    const int n0 = n_base + c * 16;
     if (n0 < N) {                                           // warp-uniform (N is a multiple of 16)
       float* mine = stage + lane * 20;
 #pragma unroll
@@ -267,16 +314,16 @@ __device__ __forceinline__ void epilogue_chunks_red(uint32_t t_row, const EpiPar
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int r = k * 8 + srow;
-        const int m = m_warp0 + r;
-        if (m < M) {
-          const float4 v = *reinterpret_cast<const float4*>(stage + r * 20 + scol);
-          long long orow = m;
-          if (p.row_period > 0 && p.remap_stride > 0)
-            orow = (long long)(m / p.row_period) * p.remap_stride + p.remap_offset + (m % p.row_period);
-          float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n0 + scol;
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                       : "memory");
+        if (rok[k]) {
+          const float4 v = *reinterpret_cast<const float4*>(stage + (k * 8 + srow) * 20 + scol);
+          float* o = orow[k] + n0;
+          if (RMW) {
+            // same single fp32 addition per element as the reduction form (resid + (acc + bias)): bit-identical
+            *reinterpret_cast<float4*>(o) = make_float4(old[k].x + v.x, old[k].y + v.y, old[k].z + v.z, old[k].w + v.w);
+          } else {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                         : "memory");
+          }
         }
       }
       __syncwarp();
@@ -542,13 +589,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       if (epi.row_period > 0 && epi.remap_stride > 0)
         out_row = (long long)(m / epi.row_period) * epi.remap_stride + epi.remap_offset +
                   (m % epi.row_period);
+      if (epi.hm_T > 0) {
+        // head-major: element offset of (sample b, head 0, token t, d 0) inside one of the q / k / v blocks
+        const int b = m / epi.hm_T, t = m - b * epi.hm_T;
+        out_row = (static_cast<long long>(b) * epi.hm_H * epi.hm_T + t) * epi.hm_hd;
+      }
       const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
       if constexpr (ROPE) {
         // BN = 256: this warp's half of the tile is one 128-wide head
         if (n_base + half * 128 < N) epilogue_rope_head(t_row + half * 128, epi, m, row_ok, n_base + half * 128);
       } else if (epi.red_inplace == 2) {
-        epilogue_chunks_red(t_row, epi, bias_s, red_stage + warp * (32 * 20), m_blk * BM + quarter * 32, M, n_base, N,
-                            half == 0 ? 0 : NCH0, half == 0 ? NCH0 : NCH);
+        epilogue_chunks_red<false>(t_row, epi, bias_s, red_stage + warp * (32 * 20), m_blk * BM + quarter * 32, M, n_base, N,
+                                   half == 0 ? 0 : NCH0, half == 0 ? NCH0 : NCH);
+      } else if (epi.red_inplace == 3) {
+        epilogue_chunks_red<true>(t_row, epi, bias_s, red_stage + warp * (32 * 20), m_blk * BM + quarter * 32, M, n_base, N,
+                                  half == 0 ? 0 : NCH0, half == 0 ? NCH0 : NCH);
       } else {
         epilogue_chunks(t_row, epi, bias_s, m, out_row, row_ok, n_base, N, half == 0 ? 0 : NCH0,
                         half == 0 ? NCH0 : NCH);
@@ -715,8 +770,21 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   // it.  CGPT_GEMM_RED_DIRECT=1 / CGPT_GEMM_RED_COALESCED=1 force one form for experiments.
   if (p.red_inplace && p.ldo % 4 == 0 && !getenv("CGPT_GEMM_RED_DIRECT") &&
       (K <= 2048 || getenv("CGPT_GEMM_RED_COALESCED")))
-    p.red_inplace = 2;
+    p.red_inplace = getenv("CGPT_GEMM_RED_NO_RMW") ? 2 : 3;   // 3 = coalesced load + add + store (A/B switch keeps the RED form)
+  if (p.red_inplace && p.ldo % 4 == 0 && getenv("CGPT_GEMM_RMW_ALL")) p.red_inplace = 3;   // experiment: RMW for the long-K GEMMs too
   p.dbg = reinterpret_cast<long long*>(getenv("CGPT_GEMM_DBG") ? strtoull(getenv("CGPT_GEMM_DBG"), nullptr, 0) : 0ull);
+  p.hm_T = 0; p.hm_H = 0; p.hm_hd = 0; p.hm_D = 0; p.hm_inv_hd = 0.f; p.hm_ws = 0;
+  if (e->hm_T > 0) {
+    CGPT_REQUIRE(e->hm_heads > 0 && e->hm_hd > 0 && e->hm_hd % 8 == 0 && N == 3 * e->hm_heads * e->hm_hd && M % e->hm_T == 0,
+                 "gemm(head-major): N = %d must be 3 * heads (%d) * hd (%d, multiple of 8) and M = %d a multiple of T = %d", N,
+                 e->hm_heads, e->hm_hd, M, e->hm_T);
+    CGPT_REQUIRE(!p.out_f32 && p.resid == nullptr && p.act == CGPT_ACT_NONE && p.row_add == nullptr && p.remap_stride == 0 &&
+                     e->rope == nullptr,
+                 "gemm(head-major): the scatter epilogue takes bf16 out, optional bias, and nothing else");
+    p.hm_T = e->hm_T; p.hm_H = e->hm_heads; p.hm_hd = e->hm_hd; p.hm_D = e->hm_heads * e->hm_hd;
+    p.hm_inv_hd = 1.0f / static_cast<float>(e->hm_hd);
+    p.hm_ws = static_cast<long long>(M) * p.hm_D;
+  }
   const cgpt_gemm_rope* rp = e->rope;
   if (rp != nullptr) {
     CGPT_REQUIRE(rp->heads > 0 && N == 3 * rp->heads * 128, "gemm(rope): N = %d must be 3 * heads * 128 (heads = %d)", N, rp->heads);

@@ -212,12 +212,21 @@ class MiniGPT4Engine:
         if collect is not None:
             collect["embed"] = res.view(B, T, v.dim).clone()
         scale = v.head_dim ** -0.5
+        # head-major q / k / v + the pipelined tcgen05 attention kernel when the shape allows (same rule as
+        # csrc/engine.cu::vit_forward; CGPT_VIT_ROW_MAJOR=1 keeps the round-1 layout for A/B runs)
+        use_hm = (not os.environ.get("CGPT_VIT_ROW_MAJOR")) and L.attn_vit_supported(B=B, H=v.heads, T=T, head_dim=v.head_dim)
+        hm = qkv.view(-1)[:3 * M * v.dim].view(3, M * v.dim)
         for i in range(v.depth):
             o = f"vit.{i}."
             L.norm_rows(res, w[o + "ln1.w"], w[o + "ln1.b"], v.eps, xn)
-            L.gemm(xn, w[o + "qkv.w"], bias=w[o + "qkv.b"], out=qkv)
-            L.attention(qkv[:, :v.dim], qkv[:, v.dim:2 * v.dim], qkv[:, 2 * v.dim:], att, B=B, H=v.heads,
-                        Tq=T, Tk=T, head_dim=v.head_dim, scale=scale)
+            if use_hm:
+                L.gemm(xn, w[o + "qkv.w"], bias=w[o + "qkv.b"], out=qkv, headmajor=(T, v.heads, v.head_dim))
+                L.attention(hm[0], hm[1], hm[2], att, B=B, H=v.heads, Tq=T, Tk=T, head_dim=v.head_dim, scale=scale,
+                            head_major=True)
+            else:
+                L.gemm(xn, w[o + "qkv.w"], bias=w[o + "qkv.b"], out=qkv)
+                L.attention(qkv[:, :v.dim], qkv[:, v.dim:2 * v.dim], qkv[:, 2 * v.dim:], att, B=B, H=v.heads,
+                            Tq=T, Tk=T, head_dim=v.head_dim, scale=scale)
             L.gemm(att, w[o + "proj.w"], bias=w[o + "proj.b"], resid=res, out=res)
             L.norm_rows(res, w[o + "ln2.w"], w[o + "ln2.b"], v.eps, xn)
             L.gemm(xn, w[o + "fc1.w"], bias=w[o + "fc1.b"], act=L.ACT_GELU, out=h)

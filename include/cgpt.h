@@ -77,6 +77,11 @@ typedef struct cgpt_gemm_epilogue {
   int remap_offset;
   int max_ctas;         /* 0 = one persistent CTA per SM                                    */
   const cgpt_gemm_rope* rope; /* NULL, or the fused rotary + KV-cache-append tail (see above)     */
+  /* hm_T > 0: HEAD-MAJOR scatter of a fused q|k|v projection (N = 3 * hm_heads * hm_hd, bf16 out, M % hm_T == 0):
+   * element (m, n) goes to out[which][b][h][t][d] with b = m / hm_T, t = m % hm_T, which = n / (heads * hd),
+   * h = (n % (heads * hd)) / hd, d = n % hd; each of the three [M / hm_T][heads][hm_T][hd] blocks is dense (ldo unused).
+   * The attention kernel then reads one contiguous block per (sample, head) (eva_vit.py:126-131). */
+  int hm_T, hm_heads, hm_hd;
 } cgpt_gemm_epilogue;
 
 int cgpt_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
@@ -189,6 +194,9 @@ typedef struct cgpt_attn_args {
   int causal;
   int decode_kernel; /* kernel selector: 0 = auto (tcgen05 one-shot kernel when the shape allows, else the
                         mma.sync flash kernel), 1 = single-token KV-cache kernel (Tq == 1), 2 = force flash */
+  int head_major;    /* 1: q, k, v are HEAD-MAJOR [B][H][T][head_dim] blocks (what the fused-QKV GEMM writes with
+                        cgpt_gemm_epilogue.hm_T; ldq / ldk / ldv unused, Tq == Tk == rows per batch): served by the
+                        pipelined tcgen05 kernel (csrc/attn_vit.cu), non-causal, <= 256 (+1 cls) keys, 64 < hd <= 128 */
 } cgpt_attn_args;
 int cgpt_attention(const cgpt_attn_args* args, void* stream);
 

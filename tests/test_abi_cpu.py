@@ -77,7 +77,7 @@ def test_ctypes_mirrors_match_the_header_structs():
         assert _struct_fields(struct) == [f[0] for f in mirror._fields_], struct
     assert ctypes.sizeof(N.ModelConfigC) == 4 * len(N.ModelConfigC._fields_)
     assert ctypes.sizeof(N.NoiseSpecC) == 56
-    assert ctypes.sizeof(L.GemmRope) == 64 and ctypes.sizeof(L.GemmEpilogue) == 104
+    assert ctypes.sizeof(L.GemmRope) == 64 and ctypes.sizeof(L.GemmEpilogue) == 120
 
 
 def test_native_engine_refuses_to_start_without_a_gpu():

@@ -117,3 +117,57 @@ def test_persistent_one_shot_kernel_many_items(lib, B, H, Tq, Tk, hd, causal, fu
     a = _run(lib, B, H, Tq, Tk, hd, causal, False, seed=3, fused_qkv=fused)
     b = _run(lib, B, H, Tq, Tk, hd, causal, True, seed=3, fused_qkv=fused)
     assert (a.float() - b.float()).abs().max().item() < 2e-2
+
+
+# ------------------------------------------------------------------ head-major layout + pipelined tcgen05 kernel (attn_vit.cu)
+def _run_head_major(lib, B, H, T, hd, seed=0):
+    """q, k, v as dense [B][H][T][hd] blocks; reference = the same fp32 softmax attention."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    q, k, v = (torch.randn(B, H, T, hd, device="cuda", generator=g).bfloat16() for _ in range(3))
+    out = torch.full((B * T, H * hd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    scale = hd ** -0.5
+    assert lib.attn_vit_supported(B=B, H=H, T=T, head_dim=hd)
+    lib.attention(q.view(-1), k.view(-1), v.view(-1), out, B=B, H=H, Tq=T, Tk=T, head_dim=hd, scale=scale, head_major=True)
+    torch.cuda.synchronize()
+    s = (q.float() @ k.float().transpose(-1, -2)) * scale
+    ref = (s.softmax(-1) @ v.float()).transpose(1, 2).reshape(B * T, H * hd)
+    assert not torch.isnan(out.float()).any(), "unwritten / NaN outputs"
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"max err {err}"
+    return out, (q, k, v)
+
+
+@pytest.mark.parametrize("B,H,T,hd", [
+    (5, 16, 257, 88),       # EVA ViT-g at 224 px: cls key / query on CUDA cores, two query tiles
+    (40, 16, 257, 88),      # 640 items: every persistent CTA pipelines several items
+    (3, 4, 17, 88),         # the small test models (img 56): one tile, 16 -> 32 padded keys masked
+    (9, 4, 100, 88),        # one query tile, 112 padded keys
+    (7, 3, 200, 96),        # two query tiles, no cls row, hd = 96
+    (6, 2, 256, 128),       # full tiles, hd = 128 (O fills the region)
+    (4, 5, 129, 72),        # second query tile holds a single row
+    (1, 1, 257, 88),        # a single item
+])
+def test_head_major_pipelined_kernel(lib, B, H, T, hd):
+    _run_head_major(lib, B, H, T, hd, seed=T + hd)
+
+
+def test_head_major_kernel_is_deterministic_and_matches_the_row_major_kernel(lib):
+    """Same inputs through the round-1 one-shot kernel (row-major fused QKV) and the pipelined head-major kernel."""
+    B, H, T, hd = 12, 16, 257, 88
+    a, (q, k, v) = _run_head_major(lib, B, H, T, hd, seed=3)
+    b, _ = _run_head_major(lib, B, H, T, hd, seed=3)
+    assert torch.equal(a, b)
+    D = H * hd
+    qkv = torch.cat([t.transpose(1, 2).reshape(B * T, D) for t in (q, k, v)], dim=1).contiguous()
+    out = torch.empty(B * T, D, device="cuda", dtype=torch.bfloat16)
+    lib.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, B=B, H=H, Tq=T, Tk=T, head_dim=hd, scale=hd ** -0.5)
+    assert (a.float() - out.float()).abs().max().item() < 1e-2
+
+
+def test_head_major_rejects_unsupported_shapes(lib):
+    q = torch.zeros(2 * 4 * 300 * 88, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(2 * 300, 4 * 88, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(lib.CgptError):
+        lib.attention(q, q, q, out, B=2, H=4, Tq=300, Tk=300, head_dim=88, scale=1.0, head_major=True)
+    with pytest.raises(lib.CgptError):
+        lib.attention(q, q, q, out, B=2, H=4, Tq=100, Tk=100, head_dim=88, scale=1.0, head_major=True, causal=True)

@@ -171,3 +171,23 @@ def test_skinny_tile_choice_is_bit_identical_to_256_wide_tiles(lib, M, N, K, kin
         _close(outs[0], _ref(a, w, torch.linspace(-1, 1, N, device="cuda")))
     else:
         _close(outs[0], _ref(a, w))
+
+
+@pytest.mark.parametrize("B,T,heads,hd", [(3, 257, 16, 88), (5, 17, 4, 88), (2, 130, 3, 96), (1, 64, 2, 128)])
+def test_head_major_qkv_scatter_epilogue(lib, B, T, heads, hd):
+    """Fused q|k|v projection written as [3][B][heads][T][hd] (what attn_vit.cu reads) = a pure permutation of the
+    row-major result: bit-identical values."""
+    g = torch.Generator(device="cuda").manual_seed(B * T)
+    D = heads * hd
+    M = B * T
+    a = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(3 * D, D, device="cuda", generator=g) / D ** 0.5).bfloat16()
+    bias = torch.randn(3 * D, device="cuda", generator=g)
+    plain = lib.gemm(a, w, bias=bias)
+    hm = torch.full((M, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lib.gemm(a, w, bias=bias, out=hm, headmajor=(T, heads, hd))
+    torch.cuda.synchronize()
+    want = plain.view(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4).contiguous()
+    assert torch.equal(hm.view(3, B, heads, T, hd), want)
+    with pytest.raises(lib.CgptError):
+        lib.gemm(a, w, bias=bias, out=hm, headmajor=(T + 1, heads, hd))

@@ -31,13 +31,16 @@ def _rel(a, b):
 
 
 def _setup(cfg, seed, max_new=3, n_classes=8, prefix=(1, 5, 6), suffix=(7, 8, 9, 10, 11), use_graphs=True,
-           early_exit=True, oracle=False):
+           early_exit=True, oracle=False, all_pairs=False):
     from certifiedgpt_b200.engine import MiniGPT4Engine
     from certifiedgpt_b200.native import NativeMiniGPT4Engine
     sd = round_to_bf16(random_state_dict(cfg, seed=seed))
     V = cfg.llm.vocab
     table = [((t,), t % (n_classes - 1)) for t in range(3, V)]
-    table += [((t, u), (t + u) % (n_classes - 1)) for t in range(3, V, 7) for u in range(3, V, 5)]
+    if all_pairs:   # every 2-token answer has its own class: label histograms of 2-token runs are not degenerate
+        table += [((t, u), (t * 7 + u) % (n_classes - 1)) for t in range(3, V) for u in range(3, V)]
+    else:
+        table += [((t, u), (t + u) % (n_classes - 1)) for t in range(3, V, 7) for u in range(3, V, 5)]
     py = MiniGPT4Engine(cfg, sd, prefix, suffix, table, n_classes, max_new_tokens=max_new, use_graphs=False,
                         early_exit=early_exit)
     nat = NativeMiniGPT4Engine.from_engine(py, use_graphs=use_graphs)
@@ -156,7 +159,9 @@ def test_certify_n0_100_n_1000_per_sample_parity_on_the_wide_config():
     equal the oracle's wherever its top-2 margin exceeds 1e-2 (north_star), counts are their histogram."""
     from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
     cfg, n_classes = WIDE, 8
-    sd, py, nat, orc = _setup(cfg, seed=31, max_new=3, n_classes=n_classes, oracle=True)
+    # 2-token answers, every (t, u) pair a class: on the CPU oracle ~80 % of the 1100 draws are margin-safe and they
+    # spread over 6 classes (122 / 102 / ... of the first 240), so the per-sample comparison is informative
+    sd, py, nat, orc = _setup(cfg, seed=31, max_new=2, n_classes=n_classes, oracle=True, all_pairs=True)
     S = cfg.vit.img_size
     x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(1000))
     n0, n, sigma, alpha = 100, 1000, 0.25, 0.001
