@@ -43,8 +43,13 @@ def parse():
     ap.add_argument("--img-size", type=int, default=224)
     ap.add_argument("--n0", type=int, default=N0)
     ap.add_argument("--n", type=int, default=N)
-    ap.add_argument("--cpu-samples", type=int, default=8,
-                    help="bounded CPU-baseline sample (noisy samples; ~10 s of host work at ~1 sample/s)")
+    ap.add_argument("--cpu-samples", type=int, default=32,
+                    help="CPU baseline = BASELINE.json configs[0]: Smooth.predict with this N (~30 s at ~1 sample/s)")
+    ap.add_argument("--sigma", type=float, default=SIGMA)
+    ap.add_argument("--images-per-pass", type=int, default=0,
+                    help="images certified together per step (0 = one per GPU: the per-rank batch stays N0+N rows)")
+    ap.add_argument("--no-decode-sweep", dest="decode_sweep", action="store_false",
+                    help="skip the max_new_tokens=20 sub-record (the reference's shipped decode budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="tiny model (debug only; not a bench number)")
     ap.add_argument("--engine", default="native", choices=["native", "python"],
@@ -123,8 +128,8 @@ def aliased_full_state_dict(cfg):
     return aliased_state_dict(cfg, seed=0)
 
 
-def cpu_reference_runner(cfg, max_new_tokens):
-    """The reference path on the host cores: oracle port of Smooth._sample_noise over the oracle
+def cpu_reference_runner(cfg, max_new_tokens, sigma=SIGMA, predict=False):
+    """The reference path on the host cores: oracle port of Smooth._sample_noise / Smooth.predict over the oracle
     MiniGPT-4 classifier (fp32, all host threads)."""
     from oracle import model_oracle as mo
     from oracle import smoothing_oracle as so
@@ -134,24 +139,29 @@ def cpu_reference_runner(cfg, max_new_tokens):
     prefix, suffix = prompt_ids(cfg.llm.vocab)
     clf = mo.MiniGPT4ClassifierOracle(sd, cfg, prefix, suffix, answer_table(cfg.llm.vocab, NUM_CLASSES),
                                       NUM_CLASSES, max_new_tokens=max_new_tokens)
-    smooth = so.SmoothOracle(clf, NUM_CLASSES, SIGMA)
+    smooth = so.SmoothOracle(clf, NUM_CLASSES, sigma)
     x = synthetic_image(0, cfg.vit.img_size)
 
     def run(samples):
         t0 = time.perf_counter()
-        counts = smooth._sample_noise(x, samples, samples)
-        dt = time.perf_counter() - t0
-        assert counts.sum() == samples
-        return dt
+        if predict:
+            run.last = int(smooth.predict(x, samples, ALPHA, 8))
+        else:
+            counts = smooth._sample_noise(x, samples, samples)
+            assert counts.sum() == samples
+        return time.perf_counter() - t0
+    run.last = None
     return run, cores
 
 
 def run_reference(args, cfg):
+    """--impl reference: the reference's CPU path on the box's host cores.  The reference is Python and /root/reference
+    does not exist on the GPU box, so what runs is the oracle PORT (fp32, all host threads) - a reported baseline."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     per_step = 2 if args.steps + args.warmup > 6 else 4   # bounded: ~1 sample/s on 16 cores
-    run, cores = cpu_reference_runner(cfg, args.max_new_tokens)
+    run, cores = cpu_reference_runner(cfg, args.max_new_tokens, args.sigma)
     for _ in range(args.warmup):
         run(per_step)
     t = sum(run(per_step) for _ in range(args.steps))
@@ -161,9 +171,9 @@ def run_reference(args, cfg):
     line = {
         "impl": "reference", "metric": "noisy_vlm_samples_per_sec", "value": sps, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "certified_images_per_min": sps * 60.0 / (args.n0 + args.n),
-        "config": workload_config(args, cfg, 1),
+        "config": workload_config(args, cfg, args.gpus),
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -171,18 +181,49 @@ def run_reference(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def images_per_pass(args, world):
+    return args.images_per_pass if args.images_per_pass > 0 else world
+
+
 def workload_config(args, cfg, world):
+    """Identical for both arms of one (--gpus, flags) invocation."""
+    K = images_per_pass(args, world)
+    per = (args.n0 + args.n + world - 1) // world
+    which = ("BASELINE.json configs[1] (Smooth.certify on 1 B200, N0=100, N=1000, sigma=0.25, 1 image)" if world == 1 and K == 1
+             else "BASELINE.json configs[2] scheme (a VQAv2-shaped synthetic subset, N=1000, noise samples of every image "
+                  "sharded across the GPUs; --gpus 8 --sigma 0.5 --steps 8 is the 64-image subset itself)")
     return {
-        "workload": (f"Smooth.certify, 1 synthetic {cfg.vit.img_size}x{cfg.vit.img_size} image, N0={args.n0}, N={args.n}, "
-                     f"sigma={SIGMA}, alpha={ALPHA}; MiniGPT-4 = EVA ViT-g/14 ({cfg.vit.depth}L) + Q-Former "
+        "workload": (f"Smooth.certify of {K} synthetic {cfg.vit.img_size}x{cfg.vit.img_size} image(s) per step, N0={args.n0}, "
+                     f"N={args.n}, sigma={args.sigma}, alpha={ALPHA}; MiniGPT-4 = EVA ViT-g/14 ({cfg.vit.depth}L) + Q-Former "
                      f"({cfg.qf.layers}L, {cfg.qf.n_query} queries) + Llama-2-7B shape ({cfg.llm.layers}L), random init; "
                      f"prompt {PREFIX_LEN}+{cfg.qf.n_query}+{SUFFIX_LEN} tokens; greedy decode max_new_tokens={args.max_new_tokens}; "
                      f"{NUM_CLASSES} classes"),
-        "baseline_config": "BASELINE.json configs[1] (Smooth.certify on 1 B200, N0=100, N=1000, sigma=0.25)",
-        "batch_size": args.batch_size, "samples_per_step": args.n0 + args.n,
-        "parallelism": f"noise draws sharded over {world} GPU(s); int64 count all-reduce",
+        "baseline_config": which,
+        "batch_size": args.batch_size, "samples_per_step": K * (args.n0 + args.n), "images_per_step": K,
+        "parallelism": (f"{K} image(s) per pass; the {args.n0 + args.n} draws of every image sharded over {world} GPU(s) "
+                        f"({per} per rank and image); one int64 all-reduce of the {K} count-vector pair(s)"),
         "l2": "per-step working set (15.7 GB bf16 weights + GBs of activations) exceeds the 126 MB L2; no explicit flush",
     }
+
+
+def calibrated_answer_table(eng, x_dev, sigma, draws, max_new_tokens, vocab):
+    """Answer vocabulary from a calibration pass (as VQAv2's 3 129 answers come from its training answers): the
+    `max_new_tokens`-token answers the model gives to `draws` noisy copies of the calibration image, ranked by
+    frequency -> class ids 0..; every other answer -> "other".  With random-init weights EOS never fires, so a table of
+    1-token answers alone would send every draw to "other" and leave the histogram degenerate."""
+    from certifiedgpt_b200 import _lib as L
+    patches = L.noise_patchify(x_dev, draws, sigma, seed=4242, stream_id=0xC0FFEE)
+    tokens = eng.vit_forward(patches)
+    queries, _ = eng.qformer_forward(tokens, want_llm_embeds=False)
+    ids, _, _ = eng.llm_prefill_decode(queries)
+    seqs = {}
+    for row in ids.cpu().tolist():
+        seqs[tuple(row)] = seqs.get(tuple(row), 0) + 1
+    ranked = sorted(seqs.items(), key=lambda kv: (-kv[1], kv[0]))
+    table = answer_table(vocab, NUM_CLASSES)
+    table += [(seq, rank % (NUM_CLASSES - 1)) for rank, (seq, _) in enumerate(ranked) if len(seq) > 1]
+    return table, {"calibration_draws": draws, "distinct_answers": len(ranked),
+                   "top_answer_share": ranked[0][1] / draws if ranked else None}
 
 
 # ------------------------------------------------------------------------------- our arm
@@ -203,18 +244,30 @@ def run_ours(args, cfg):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L.load()
+    native = args.engine == "native"
+    K = images_per_pass(args, world)
+    assert native or K == 1, "several images per pass need the native engine (cgpt_certify_batch)"
+    sigma = args.sigma
 
     sd = random_state_dict(cfg, seed=0, device=dev)
     prefix, suffix = prompt_ids(cfg.llm.vocab)
-    Engine = NativeMiniGPT4Engine if args.engine == "native" else MiniGPT4Engine
-    eng = Engine(cfg, sd, prefix, suffix, answer_table(cfg.llm.vocab, NUM_CLASSES), NUM_CLASSES,
-                 max_new_tokens=args.max_new_tokens, device=dev, early_exit=True)
+    long_new = max(args.max_new_tokens, 20) if (native and args.decode_sweep) else args.max_new_tokens
+    # the packed weights (and rotary tables long enough for the reference's max_new_tokens = 20) are built once
+    src = MiniGPT4Engine(cfg, sd, prefix, suffix, answer_table(cfg.llm.vocab, NUM_CLASSES), NUM_CLASSES,
+                         max_new_tokens=long_new, device=dev, early_exit=True, use_graphs=native is False)
     del sd
     torch.cuda.empty_cache()
-    smooth = Smooth(eng, NUM_CLASSES, SIGMA, seed=42, process_group=True if world > 1 else None)
-    x_host = synthetic_image(0, cfg.vit.img_size).pin_memory()
-    x_dev = x_host.to(dev)
-    per_step = args.n0 + args.n
+    eng = NativeMiniGPT4Engine.from_engine(src, max_new_tokens=args.max_new_tokens, early_exit=True) if native else src
+    x_hosts = [synthetic_image(i, cfg.vit.img_size).pin_memory() for i in range(K)]
+    x_devs = [x.to(dev) for x in x_hosts]
+    per_image = args.n0 + args.n
+    per_step = K * per_image
+    calib = None
+    if native:
+        table, calib = calibrated_answer_table(eng, x_devs[0], sigma, min(per_image, args.batch_size),
+                                               args.max_new_tokens, cfg.llm.vocab)
+        eng.set_answer_table(table)
+    smooth = Smooth(eng, NUM_CLASSES, sigma, seed=42, process_group=True if world > 1 else None)
 
     def barrier():
         if world > 1:
@@ -234,21 +287,27 @@ def run_ours(args, cfg):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    def step_resident():
-        return smooth.certify(x_dev, args.n0, args.n, ALPHA, args.batch_size)
+    def certify_step(sm, xs):
+        if K == 1:
+            return [sm.certify(xs[0], args.n0, args.n, ALPHA, args.batch_size)]
+        return sm.certify_batch(xs, args.n0, args.n, ALPHA, args.batch_size)
 
-    x_stage = torch.empty_like(x_dev)
+    def step_resident():
+        return certify_step(smooth, x_devs)
+
+    x_stage = torch.empty_like(x_devs[0])
 
     def step_e2e():
-        if args.engine == "native":
-            # HOST buffers straight through the C-ABI: cgpt_certify stages x (H2D from pinned memory) and reads
-            # back (label, radius, cAHat, pABar, nA) - both copies inside the timed region
-            return smooth.certify(x_host, args.n0, args.n, ALPHA, args.batch_size)
-        x_stage.copy_(x_host, non_blocking=True)          # H2D of the step's input from pinned memory
-        return smooth.certify(x_stage, args.n0, args.n, ALPHA, args.batch_size)   # D2H of (label, radius)
+        if native:
+            # HOST buffers straight through the C-ABI: cgpt_certify(_batch) stages the image(s) (H2D from pinned
+            # memory) and reads back (label, radius, cAHat, pABar, nA) per image - both copies inside the timed region
+            return certify_step(smooth, x_hosts)
+        x_stage.copy_(x_hosts[0], non_blocking=True)      # H2D of the step's input from pinned memory
+        return certify_step(smooth, [x_stage])            # D2H of (label, radius)
 
     for _ in range(args.warmup):
         step_resident()
+
     def n_launches():   # libcgpt counts eager launches and replayed graph nodes; the python engine counts its replays
         return L.launch_count() + getattr(eng, "replayed_launches", 0)
 
@@ -258,23 +317,49 @@ def run_ours(args, cfg):
     launches = n_launches() - launches0
     ms_e2e = timed(step_e2e, args.steps)
     result = step_resident()
+    detail = smooth.last_batch_detail[0] if K > 1 else {"counts_estimation": smooth.last_counts_estimation}
+    counts_est = detail["counts_estimation"]
+    decode_steps = eng.last_steps
+
     # roofline pass: the same steps launched eagerly (not as graph replays) so that every GEMM launch can be
     # bracketed by a CUDA-event pair on its stream; same kernels, same shapes, same data
-    def set_graphs(on):
-        if args.engine == "native":
-            eng.set_option("use_graphs", on)
+    def set_graphs(e_, on):
+        if native:
+            e_.set_option("use_graphs", on)
         else:
-            eng.use_graphs = on
+            e_.use_graphs = on
 
-    set_graphs(False)
+    set_graphs(eng, False)
     step_resident()
     L.gemm_profile_start()
     ms_prof = timed(step_resident, args.steps)
     prof = L.gemm_profile_stop()
-    set_graphs(True)
+    set_graphs(eng, True)
 
     value = per_step * args.steps / (ms / 1e3)
     e2e = per_step * args.steps / (ms_e2e / 1e3)
+
+    # the reference's shipped decode budget (max_new_tokens = 20, configs/eval_configs/vqav2_eval_noise_0.yaml:44) next to
+    # the short-answer budget of the headline: same weights, same image(s), workspace re-bound for the longer KV cache
+    decode = {f"max_new_tokens_{args.max_new_tokens}": {"samples_per_s": value, "ms_per_step": ms / args.steps,
+                                                        "decode_steps_run": decode_steps}}
+    if native and args.decode_sweep and long_new > args.max_new_tokens:
+        try:
+            eng._ws = None
+            del smooth, eng
+            torch.cuda.empty_cache()
+            eng = NativeMiniGPT4Engine.from_engine(src, max_new_tokens=long_new, early_exit=True)
+            sm20 = Smooth(eng, NUM_CLASSES, sigma, seed=42, process_group=True if world > 1 else None)
+            steps20 = max(1, min(args.steps, 3))
+            for _ in range(2):
+                certify_step(sm20, x_devs)
+            ms20 = timed(lambda: certify_step(sm20, x_devs), steps20)
+            decode[f"max_new_tokens_{long_new}"] = {"samples_per_s": per_step * steps20 / (ms20 / 1e3),
+                                                    "ms_per_step": ms20 / steps20, "decode_steps_run": eng.last_steps,
+                                                    "steps_timed": steps20,
+                                                    "note": "random-init weights never emit EOS: all 20 steps always run"}
+        except Exception as ex:   # the headline must still be reported
+            decode[f"max_new_tokens_{long_new}"] = {"failed": f"{type(ex).__name__}: {ex}"}
 
     # roofline of the dominant kernel (gemm_bf16_tcgen05_kernel, all launches of the timed region)
     gemm_ms = sum(p[0] for p in prof)
@@ -306,17 +391,20 @@ def run_ours(args, cfg):
         pass
 
     if rank == 0:
+        img_bytes = x_hosts[0].numel() * 4
         line = {
             "metric": "noisy_vlm_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args, cfg, world),
-            "certified_images_per_min": value * 60.0 / per_step,
-            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": 32 if args.engine == "native" else 24,
-                    "certified_images_per_min": e2e * 60.0 / per_step,
-                    "api": ("Smooth.certify(x_host) -> cgpt_certify (C-ABI, host x, host label/radius)"
-                            if args.engine == "native" else "Smooth.certify(x_dev) after an explicit pinned H2D copy")},
+            "certified_images_per_min": value * 60.0 / per_image,
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": K * img_bytes,
+                    "d2h_bytes_per_step": K * (36 if native and K > 1 else (32 if native else 24)),
+                    "certified_images_per_min": e2e * 60.0 / per_image,
+                    "api": ((("Smooth.certify(x_host) -> cgpt_certify" if K == 1 else
+                              "Smooth.certify_batch(x_hosts) -> cgpt_certify_batch") +
+                             " (C-ABI, host images, host labels / radii)")
+                            if native else "Smooth.certify(x_dev) after an explicit pinned H2D copy")},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the timed steps)",
@@ -327,18 +415,25 @@ def run_ours(args, cfg):
                          "gemm_launches": len(prof),
                          "top_shapes": {k: {"ms": round(v[0], 3), "tflops": round(v[1] / (v[0] / 1e3) / 1e12, 1), "launches": v[2]}
                                         for k, v in top}},
-            "result": {"label": result[0], "radius": result[1], "decode_steps": eng.last_steps},
+            "result": {"label": result[0][0], "radius": result[0][1], "decode_steps": decode_steps,
+                       "classes_hit": int((counts_est > 0).sum()), "top_count": int(counts_est.max()),
+                       "answer_table": calib},
+            "decode": decode,
             "engine": args.engine,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                run, cores = cpu_reference_runner(cfg, args.max_new_tokens)
+                # BASELINE.json configs[0] as stated: Smooth.predict on the host cores, 1 image + question, N = 32,
+                # sigma = 0.25, 1-token answer head, batch 8 (the reference's own CPU-runnable case)
+                run, cores = cpu_reference_runner(cfg, 1, 0.25, predict=True)
                 run(1)
                 dt = run(args.cpu_samples)
                 line["cpu_baseline"] = {
                     "value": args.cpu_samples / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-                    "sample": (f"{args.cpu_samples} noisy samples of the same workload through the oracle port "
-                               f"(fp32 torch CPU, {cores} threads, layer weights aliased), after 1 warm-up sample")}
+                    "sample": (f"BASELINE.json configs[0]: Smooth.predict, 1 synthetic 224x224 image + question, N = "
+                               f"{args.cpu_samples}, sigma = 0.25, batch 8, 1-token answer head, through the oracle port "
+                               f"(fp32 torch CPU, {cores} threads, layer weights aliased), after 1 warm-up sample; "
+                               f"result = {run.last}")}
             except Exception as ex:  # the GPU number must still be reported
                 line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {type(ex).__name__}: {ex}"}

@@ -8,16 +8,18 @@
 //
 // One persistent CTA per SM walks its items as a software pipeline over (item, 128-query tile) units:
 //   warp 0     TMA producer : Q tile(s), K, V of item i+1 into the slots item i has released (+ L2 prefetch of i+2)
-//   warp 1     MMA issuer   : one thread, a polling state machine over the two TMEM regions:
+//   warp 1     MMA issuer   : one thread, over the two TMEM regions:
 //                               S_t = Q_t K^T  (UMMA 128 x nk x 16, fp32 in TMEM region t, 256 columns)
 //                               O_t = P_t V    (A operand = P_t READ FROM TMEM, B = V in place, MN-major)
 //   warps 4-7  softmax of q-tile 0, warps 8-11 softmax of q-tile 1 (thread = query row): row max, exp2, and the
 //              unnormalised P as packed bf16 written IN PLACE over the first 128 columns of its own S region with
 //              tcgen05.st (no shared-memory P tile, no proxy fence); O_t lands in columns 128.. of the same region.
 //   warps 2-3  the cls QUERY row on CUDA cores (scores from the softmax threads, P.V as a GEMV out of the V tile)
-// S_t of item i+1 is issued as soon as O_t of item i has been drained, so the tensor core, the two softmax groups
-// (MUFU-bound) and the loads of the next item overlap; the cls KEY is folded in on CUDA cores (one extra score per
-// row + a rank-1 update of O) so every tensor-core tile is exactly 128 x 256.
+// S_t of item i+1 is issued as soon as O_t of item i has been drained, and the softmax threads compute the cls scores
+// of item i+1 while P_t.V of item i runs, so the tensor core, the softmax groups (MUFU-bound) and the loads of the next
+// item overlap; the cls KEY is folded in on CUDA cores (one extra score per row + a rank-1 update of O) so every
+// tensor-core tile is exactly 128 x 256.  O leaves through a per-warp shared-memory transpose: every global store
+// instruction writes 8 rows x 64 contiguous bytes instead of 32 rows x 16.
 #include <stdlib.h>
 #include "common.cuh"
 #include "ops.h"
@@ -85,6 +87,8 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
   constexpr int XBUF = 3 * 128 + 320;                  // [xk 128 | xv 128 | xq 128 | xs 320] fp32
   float* xbase = reinterpret_cast<float*>(tail + 256);
   float* xo = xbase + 2 * XBUF;                        // cls-query partial outputs [5][96+]
+  constexpr int OPITCH = 80;                           // bytes per staged row: 32 bf16 + 16 B pad (conflict-free 16-byte writes)
+  uint8_t* ostage = reinterpret_cast<uint8_t*>(xo + 5 * 96 + 32);   // [8 softmax warps][32 rows][OPITCH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #define VA_STAMP(slot) do { if (p.dbg) p.dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
@@ -214,36 +218,25 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
         issue_s(t);
       }
       VA_STAMP(2);
-      int st[2] = {0, 0}, it_t[2] = {0, 0};
-      int done = 0;
-      while (done < nqt) {
-        bool progress = false;
+      // both softmax groups run in lockstep (same item, same phase), so the natural order is fixed:
+      // P.V of both tiles as their P arrives, then S of the next item for each tile as its region drains
+      for (int it = 0; it < n_mine; ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(bar_v, ph);
         for (int t = 0; t < nqt; ++t) {
-          const uint32_t ph = it_t[t] & 1;
-          if (st[t] == 0) {
-            // P_t of item it_t[t] written by its softmax group, V of that item in shared memory
-            if (mbar_test(&bar_p[t], ph) && mbar_test(bar_v, ph)) {
-              tcgen05_fence_after();
-              issue_pv(t);
-              st[t] = 1;
-              progress = true;
-            }
-          } else if (st[t] == 1) {
-            if (it_t[t] + 1 >= n_mine) {
-              st[t] = 2;
-              ++done;
-              progress = true;
-            } else if (mbar_test(&bar_free[t], ph) && mbar_test(&bar_q[t], ph ^ 1) && mbar_test(bar_k, ph ^ 1)) {
-              // region t drained, Q tile t and K of the next item landed
-              tcgen05_fence_after();
-              issue_s(t);
-              ++it_t[t];
-              st[t] = 0;
-              progress = true;
-            }
+          mbar_wait(&bar_p[t], ph);
+          tcgen05_fence_after();
+          issue_pv(t);
+        }
+        if (it + 1 < n_mine) {
+          mbar_wait(bar_k, ph ^ 1);
+          for (int t = 0; t < nqt; ++t) {
+            mbar_wait(&bar_free[t], ph);       // region t drained by its softmax group
+            mbar_wait(&bar_q[t], ph ^ 1);      // Q tile t of the next item landed
+            tcgen05_fence_after();
+            issue_s(t);
           }
         }
-        if (!progress) __nanosleep(32);
       }
       VA_STAMP(3);
     }
@@ -258,7 +251,10 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
         float* xb = xbase + (it & 1) * XBUF;
         float* xk = xb; float* xv = xb + 128; float* xq = xb + 256; float* xs = xb + 384;
         if (warp == 3) {
-          // stage this item's cls key / value / query as fp32; the buffer was last used two items ago
+          // stage this item's cls key / value / query as fp32; the buffer was last used two items ago, whose
+          // epilogue (the rank-1 cls term reads xv) runs AFTER the softmax threads' cls scores of item it - 1
+          if (it >= 2)
+            for (int t = 0; t < nqt; ++t) mbar_wait(&bar_free[t], ph);
           const long long row0 = static_cast<long long>(item) * T * hd;
           if (lane < 16) {
             const bool ok = lane * 8 < hd;
@@ -345,44 +341,58 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
       const bool row_ok = q_main < Tq_main;
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + t * 256;
       const int kmax = Tk_main;                        // main keys [0, kmax) visible (padded keys masked)
+      uint8_t* patch = ostage + (warp - 4) * (32 * OPITCH);
+      // Scores against the cls key (this row, returned) and of the cls query against main key q_main (thread <-> key,
+      // into xs), read from the TMA-loaded, swizzled Q / K tiles in shared memory.  All the 16-byte loads of a row are
+      // issued before the first multiply (hd <= 96: at most 12 chunks).
+      auto cls_scores = [&](int it) -> float {
+        const uint32_t ph = it & 1;
+        float* xb = xbase + (it & 1) * XBUF;
+        const float* xk = xb; const float* xq = xb + 256; float* xs = xb + 384;
+        mbar_wait(&bar_xr[it & 1], (it >> 1) & 1);
+        mbar_wait(&bar_q[t], ph);
+        mbar_wait(bar_k, ph);
+        const int nch = hd >> 3;
+        const uint8_t* qrow = sQ + t * 2 * VSUB + r * 128;
+        const uint8_t* krow = sK + q_main * 128;          // key index == q_main (requires q_main < nk_pad)
+        const bool kok = q_main < Tk_main;
+        uint4 tile[12];
+        auto dot = [&](const float* x) {
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 12; ++c) {
+            if (c < nch) {
+              const float4 x0 = *reinterpret_cast<const float4*>(x + c * 8), x1 = *reinterpret_cast<const float4*>(x + c * 8 + 4);
+              acc += bf16_lo(tile[c].x) * x0.x + bf16_hi(tile[c].x) * x0.y + bf16_lo(tile[c].y) * x0.z + bf16_hi(tile[c].y) * x0.w +
+                     bf16_lo(tile[c].z) * x1.x + bf16_hi(tile[c].z) * x1.y + bf16_lo(tile[c].w) * x1.z + bf16_hi(tile[c].w) * x1.w;
+            }
+          }
+          return acc;
+        };
+#pragma unroll
+        for (int c = 0; c < 12; ++c)
+          if (c < nch) tile[c] = *reinterpret_cast<const uint4*>(qrow + (c >> 3) * VSUB + (((c & 7) ^ (r & 7)) << 4));
+        const float a1 = dot(xk);
+        if (kok) {
+#pragma unroll
+          for (int c = 0; c < 12; ++c)
+            if (c < nch) tile[c] = *reinterpret_cast<const uint4*>(krow + (c >> 3) * kv_sub + (((c & 7) ^ (q_main & 7)) << 4));
+          xs[1 + q_main] = dot(xq);
+        }
+        mbar_arrive(bar_x);
+        return row_ok ? a1 : -INFINITY;
+      };
+      float s_x = -INFINITY;
+      if (n_mine > 0) {
+        if (E) s_x = cls_scores(0);
+        mbar_arrive(bar_qkr);              // this thread no longer reads the Q / K tiles of item 0
+      }
       int it = 0;
       for (int item = first_item; item < p.n_items; item += grid, ++it) {
         const uint32_t ph = it & 1;
         const int h = item % p.H, b = item / p.H;
-        float* xb = xbase + (it & 1) * XBUF;
-        float* xk = xb; float* xv = xb + 128; float* xq = xb + 256; float* xs = xb + 384;
+        const float* xv = xbase + (it & 1) * XBUF + 128;
         if (threadIdx.x == 128) VA_STAMP(5);
-        // scores against the cls key (this row) and of the cls query against main key q_main (thread <-> key),
-        // read from the TMA-loaded, swizzled Q / K tiles in shared memory while the S products run
-        float s_x = -INFINITY;
-        if (E) {
-          mbar_wait(&bar_xr[it & 1], (it >> 1) & 1);
-          mbar_wait(&bar_q[t], ph);
-          mbar_wait(bar_k, ph);
-          float a1 = 0.f, a2 = 0.f;
-          const int nch = hd >> 3;
-          const uint8_t* qrow = sQ + t * 2 * VSUB + r * 128;
-          const uint8_t* krow = sK + q_main * 128;        // key index == q_main (requires q_main < nk_pad)
-          const bool kok = q_main < Tk_main;
-          for (int c = 0; c < nch; ++c) {
-            const int sub = c >> 3, cc = c & 7;
-            const uint4 qv = *reinterpret_cast<const uint4*>(qrow + sub * VSUB + ((cc ^ (r & 7)) << 4));
-            const float4 k0 = *reinterpret_cast<const float4*>(xk + c * 8), k1 = *reinterpret_cast<const float4*>(xk + c * 8 + 4);
-            a1 += bf16_lo(qv.x) * k0.x + bf16_hi(qv.x) * k0.y + bf16_lo(qv.y) * k0.z + bf16_hi(qv.y) * k0.w +
-                  bf16_lo(qv.z) * k1.x + bf16_hi(qv.z) * k1.y + bf16_lo(qv.w) * k1.z + bf16_hi(qv.w) * k1.w;
-            if (kok) {
-              const uint4 kv = *reinterpret_cast<const uint4*>(krow + sub * kv_sub + ((cc ^ (q_main & 7)) << 4));
-              const float4 q0 = *reinterpret_cast<const float4*>(xq + c * 8), q1 = *reinterpret_cast<const float4*>(xq + c * 8 + 4);
-              a2 += bf16_lo(kv.x) * q0.x + bf16_hi(kv.x) * q0.y + bf16_lo(kv.y) * q0.z + bf16_hi(kv.y) * q0.w +
-                    bf16_lo(kv.z) * q1.x + bf16_hi(kv.z) * q1.y + bf16_lo(kv.w) * q1.z + bf16_hi(kv.w) * q1.w;
-            }
-          }
-          if (row_ok) s_x = a1;
-          if (kok) xs[1 + q_main] = a2;
-          mbar_arrive(bar_x);
-        }
-        mbar_arrive(bar_qkr);                // this thread no longer reads the Q / K tiles of this item
-        if (threadIdx.x == 128) VA_STAMP(6);
         mbar_wait(&bar_s[t], ph);
         if (threadIdx.x == 128) VA_STAMP(7);
         tcgen05_fence_after();
@@ -463,49 +473,53 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
         tcgen05_fence_before();     // ... and are ordered before the P.V product the MMA thread issues after the barrier
         mbar_arrive(&bar_p[t]);
         if (threadIdx.x == 128) VA_STAMP(9);
-        // ---- epilogue: O_t / rowsum (+ the cls key's rank-1 term) -> bf16 -> global
+        // while P_t.V runs: the cls scores of the NEXT item (its Q tile and K landed long ago)
+        if (item + grid < p.n_items) {
+          if (E) s_x = cls_scores(it + 1);
+          mbar_arrive(bar_qkr);              // this thread no longer reads the Q / K tiles of item it + 1
+        }
+        if (threadIdx.x == 128) VA_STAMP(12);
+        // ---- epilogue: O_t / rowsum (+ the cls key's rank-1 term) -> bf16 -> shared-memory transpose -> global
         mbar_wait(&bar_o[t], ph);
         if (threadIdx.x == 128) VA_STAMP(10);
         tcgen05_fence_after();
         const float inv = sum > 0.f ? 1.f / sum : 0.f;
         const uint32_t o_addr = t_lane + 128;
-        __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * T + E + q_main) * p.ldo + h * hd;
-        auto store16 = [&](const uint32_t* v, int c) {
-          if (!row_ok) return;
-          float f[16];
-          if (E) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 x4 = *reinterpret_cast<const float4*>(xv + ((c + i) & 127));
-              f[i] = (__uint_as_float(v[i]) + p_x * x4.x) * inv;
-              f[i + 1] = (__uint_as_float(v[i + 1]) + p_x * x4.y) * inv;
-              f[i + 2] = (__uint_as_float(v[i + 2]) + p_x * x4.z) * inv;
-              f[i + 3] = (__uint_as_float(v[i + 3]) + p_x * x4.w) * inv;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv;
-          }
-          *reinterpret_cast<uint4*>(orow + c) =
-              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-          if (c + 8 < hd)
-            *reinterpret_cast<uint4*>(orow + c + 8) =
-                make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-        };
-        {
-          uint32_t va[16], vb[16];
-          tmem_ld_x16(o_addr, va);
+        // row served by this lane on the way out: (lane >> 2) + 8 * k of the warp's 32 rows, 16-byte segment lane & 3
+        const int q_warp0 = t * 128 + (warp & 3) * 32;
+        __nv_bfloat16* obase = p.o + (static_cast<long long>(b) * T + E + q_warp0) * p.ldo + h * hd;
 #pragma unroll 1
-          for (int c = 0; c < hd; c += 32) {
-            tmem_ld_wait();
-            if (c + 16 < hd) tmem_ld_x16(o_addr + c + 16, vb);
-            store16(va, c);
-            if (c + 16 < hd) {
-              tmem_ld_wait();
-              if (c + 32 < hd) tmem_ld_x16(o_addr + c + 32, va);
-              store16(vb, c + 16);
+        for (int c = 0; c < hd; c += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(o_addr + c, v);
+          tmem_ld_wait();
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float f0 = __uint_as_float(v[i]), f1 = __uint_as_float(v[i + 1]);
+            if (E) {
+              f0 += p_x * xv[(c + i) & 127];
+              f1 += p_x * xv[(c + i + 1) & 127];
+            }
+            w[i >> 1] = pack_bf16x2(f0 * inv, f1 * inv);
+          }
+          uint4* mine = reinterpret_cast<uint4*>(patch + lane * OPITCH);
+          mine[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          mine[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          mine[2] = make_uint4(w[8], w[9], w[10], w[11]);
+          mine[3] = make_uint4(w[12], w[13], w[14], w[15]);
+          __syncwarp();
+          const int seg = lane & 3;
+          if (c + seg * 8 < hd) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = k * 8 + (lane >> 2);
+              if (q_warp0 + rr < Tq_main)
+                *reinterpret_cast<uint4*>(obase + static_cast<long long>(rr) * p.ldo + c + seg * 8) =
+                    *reinterpret_cast<const uint4*>(patch + rr * OPITCH + seg * 16);
             }
           }
+          __syncwarp();
         }
         tcgen05_fence_before();     // this thread's TMEM reads of O_t are done before the next S_t may overwrite the region
         mbar_arrive(&bar_free[t]);
@@ -592,7 +606,8 @@ int attention_vit(const cgpt_attn_args* a, cudaStream_t stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int kv_sub = p.nk_pad * 128;
-  const int smem = p.n_qtiles * 2 * VSUB + 4 * kv_sub + 256 + (2 * (3 * 128 + 320) + 5 * 96 + 32) * 4 + 1024;
+  const int smem = p.n_qtiles * 2 * VSUB + 4 * kv_sub + 256 + (2 * (3 * 128 + 320) + 5 * 96 + 32) * 4 +
+                   8 * 32 * 80 /* epilogue transpose patches */ + 1024;
   CGPT_REQUIRE(smem <= 227 * 1024, "attention_vit: shared memory %d too large", smem);
   const long long rows = (long long)a->B * a->H * a->Tk;
   CUtensorMap mq0, mq1, mk0, mk1, mv0, mv1;

@@ -122,7 +122,7 @@ struct Buffers {   // all inside the caller's workspace
 };
 
 struct GraphSet {
-  int B, space, kind;
+  int B, K, space, kind;   // K = images per pass (B / K draws of each)
   float mean[3], std[3];
   cudaGraphExec_t g0 = nullptr;
   std::vector<cudaGraphExec_t> steps;
@@ -172,6 +172,7 @@ struct cgpt_engine {
   int32_t* h_i32 = nullptr;   // [8]
   double* h_f64 = nullptr;    // [8]
   int last_steps = 0;
+  int max_images = 1;            // images per pass the workspace serves (cgpt_set_option "max_images", before binding)
   const double* lut = nullptr;   // cgpt_set_radius_lut: [pABar | Phi^-1(pABar)] for (lut_n, lut_alpha), caller-owned
   long long lut_n = 0;
   double lut_alpha = 0.0;
@@ -337,12 +338,13 @@ long long layout(Engine* E, int B, bool encoder_only, char* base, Buffers* out) 
   const long long D = c.vit_dim, Hq = c.qf_hidden, Hl = c.llm_hidden;
   Buffers b;
   memset(&b, 0, sizeof(b));
-  b.x_static = static_cast<float*>(take(3LL * c.img_size * c.img_size * 4));
-  b.dyn = take(sizeof(NoiseDyn));
-  b.counts = static_cast<long long*>(take(2LL * c.num_classes * 8));
+  const long long KI = E->max_images;
+  b.x_static = static_cast<float*>(take(KI * 3LL * c.img_size * c.img_size * 4));   // [max_images][3, S, S]
+  b.dyn = take(KI * sizeof(NoiseDyn));
+  b.counts = static_cast<long long*>(take(KI * 2LL * c.num_classes * 8));           // [max_images][2][num_classes]
   b.invalid = static_cast<int32_t*>(take(4));
-  b.tail_label = static_cast<int32_t*>(take(3 * 4));
-  b.tail_stats = static_cast<double*>(take(3 * 8));
+  b.tail_label = static_cast<int32_t*>(take(KI * 3 * 4));
+  b.tail_stats = static_cast<double*>(take(KI * 3 * 8));
   b.patches = take(static_cast<long long>(B) * E->Pn * 592 * 2);
   b.v_res = take(Mv * D * 4);
   b.v_xn = take(Mv * D * 2);
@@ -687,17 +689,28 @@ int capture_end(Engine* E, int body_rc, cudaGraphExec_t* exec) {
   return 0;
 }
 
-int get_graphs(Engine* E, const cgpt_noise_spec* n, int B, cudaStream_t s, GraphSet** out) {
+// K1 for a pass over K images: segment k = B / K draws of the image at x_static[k], noise parameters from dyn[k]
+int noise_segments(Engine* E, const cgpt_noise_spec* n, int B, int K, cudaStream_t s) {
+  const Buffers& b = E->b;
+  const int per = B / K;
+  const long long img_elems = 3LL * E->c.img_size * E->c.img_size;
+  for (int k = 0; k < K; ++k)
+    CGPT_TRY(noise_patchify(b.x_static + k * img_elems, nullptr, 0, 0, 0, per, 0.f, n->mean, n->std, n->noise_space,
+                            n->noise_kind, E->c.img_size, bf(b.patches) + static_cast<long long>(k) * per * E->Pn * 592,
+                            592, static_cast<const NoiseDyn*>(b.dyn) + k, s));
+  return 0;
+}
+
+int get_graphs(Engine* E, const cgpt_noise_spec* n, int B, int K, cudaStream_t s, GraphSet** out) {
   for (auto& g : E->graphs)
-    if (g.B == B && g.space == n->noise_space && g.kind == n->noise_kind && !memcmp(g.mean, n->mean, 12) &&
+    if (g.B == B && g.K == K && g.space == n->noise_space && g.kind == n->noise_kind && !memcmp(g.mean, n->mean, 12) &&
         !memcmp(g.std, n->std, 12)) {
       *out = &g;
       return 0;
     }
   const Buffers& b = E->b;
   // warm-up outside capture (first-use cudaFuncSetAttribute calls), on the caller's stream
-  CGPT_TRY(noise_patchify(b.x_static, nullptr, 0, 0, 0, B, 0.f, n->mean, n->std, n->noise_space, n->noise_kind,
-                          E->c.img_size, b.patches, 592, b.dyn, s));
+  CGPT_TRY(noise_segments(E, n, B, K, s));
   CGPT_TRY(vit_forward(E, b.patches, B, b.v_out, s));
   CGPT_TRY(qformer_forward(E, b.v_out, B, b.q_h, s));
   CGPT_TRY(llm_prefill_first(E, b.q_h, B, s));
@@ -705,15 +718,14 @@ int get_graphs(Engine* E, const cgpt_noise_spec* n, int B, cudaStream_t s, Graph
   CGPT_CHECK_CUDA(cudaStreamSynchronize(s));
 
   GraphSet gs;
-  gs.B = B; gs.space = n->noise_space; gs.kind = n->noise_kind;
+  gs.B = B; gs.K = K; gs.space = n->noise_space; gs.kind = n->noise_kind;
   memcpy(gs.mean, n->mean, 12);
   memcpy(gs.std, n->std, 12);
   cudaStream_t cs = E->cap_stream;
   const long long c_start = total_launch_count();
   long long c0 = c_start;
   CGPT_TRY(capture_begin(E));
-  int rc = noise_patchify(b.x_static, nullptr, 0, 0, 0, B, 0.f, n->mean, n->std, n->noise_space, n->noise_kind,
-                          E->c.img_size, b.patches, 592, b.dyn, cs);
+  int rc = noise_segments(E, n, B, K, cs);
   if (!rc) rc = vit_forward(E, b.patches, B, b.v_out, cs);
   if (!rc) rc = qformer_forward(E, b.v_out, B, b.q_h, cs);
   if (!rc) rc = llm_prefill_first(E, b.q_h, B, cs);
@@ -748,7 +760,7 @@ int noisy_labels(Engine* E, const float* x_dev, const cgpt_noise_spec* n, uint64
     // pageable source: staged before the call returns, so the stack bytes can die at once
     CGPT_CHECK_CUDA(cudaMemcpyAsync(b.dyn, &d, sizeof(d), cudaMemcpyHostToDevice, s));
     GraphSet* g = nullptr;
-    CGPT_TRY(get_graphs(E, n, B, s, &g));
+    CGPT_TRY(get_graphs(E, n, B, 1, s, &g));
     CGPT_CHECK_CUDA(cudaGraphLaunch(g->g0, s));
     count_launch(g->nodes[0]);
     int steps = 1;
@@ -764,6 +776,47 @@ int noisy_labels(Engine* E, const float* x_dev, const cgpt_noise_spec* n, uint64
   } else {
     const float* eps = n->eps ? n->eps + static_cast<long long>(first) * img_elems : nullptr;
     CGPT_TRY(stage0_eager(E, x_dev, eps, n, first, B, s));
+    CGPT_TRY(llm_generate(E, b.q_h, B, s));
+  }
+  return labels_of_ids(E, B, labels, s);
+}
+
+// One pass over K images (already staged in x_static[0..K)): `per` draws of each, global sample indices
+// [first, first + per) of every image, image k drawn from Philox stream stream_id + k.  labels: [K * per], image-major.
+int noisy_labels_images(Engine* E, const cgpt_noise_spec* n, uint64_t first, int K, int per, int32_t* labels,
+                        cudaStream_t s) {
+  const int B = K * per;
+  CGPT_TRY(check_ready(E, B, true));
+  CGPT_REQUIRE(K >= 1 && K <= E->max_images, "engine: %d images per pass, the workspace serves %d (option max_images)", K,
+               E->max_images);
+  CGPT_REQUIRE(n->eps == nullptr, "engine: injected noise is a single-image (parity) feature");
+  const Buffers& b = E->b;
+  std::vector<NoiseDyn> d(K);
+  for (int k = 0; k < K; ++k) {
+    d[k].seed = n->seed; d[k].first_sample = first; d[k].stream_id = n->stream_id + static_cast<uint32_t>(k);
+    d[k].sigma = n->sigma;
+  }
+  // pageable source: staged before the call returns, so the host vector can die at once
+  CGPT_CHECK_CUDA(cudaMemcpyAsync(b.dyn, d.data(), K * sizeof(NoiseDyn), cudaMemcpyHostToDevice, s));
+  if (E->c.use_graphs) {
+    GraphSet* g = nullptr;
+    CGPT_TRY(get_graphs(E, n, B, K, s, &g));
+    CGPT_CHECK_CUDA(cudaGraphLaunch(g->g0, s));
+    count_launch(g->nodes[0]);
+    int steps = 1;
+    for (int t = 1; t < E->c.max_new_tokens; ++t) {
+      bool done;
+      CGPT_TRY(all_finished(E, s, &done));
+      if (done) break;
+      CGPT_CHECK_CUDA(cudaGraphLaunch(g->steps[t - 1], s));
+      count_launch(g->nodes[t]);
+      steps = t + 1;
+    }
+    E->last_steps = steps;
+  } else {
+    CGPT_TRY(noise_segments(E, n, B, K, s));
+    CGPT_TRY(vit_forward(E, b.patches, B, b.v_out, s));
+    CGPT_TRY(qformer_forward(E, b.v_out, B, b.q_h, s));
     CGPT_TRY(llm_generate(E, b.q_h, B, s));
   }
   return labels_of_ids(E, B, labels, s);
@@ -886,8 +939,8 @@ int cgpt_create(const cgpt_model_config* cfg, cgpt_handle* out) {
   E->Tp = c.qf_queries + c.n_suffix;
   E->cache_rows = E->P + E->Tp + c.max_new_tokens;
   if (cudaStreamCreateWithFlags(&E->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost(reinterpret_cast<void**>(&E->h_i32), 8 * sizeof(int32_t)) != cudaSuccess ||
-      cudaMallocHost(reinterpret_cast<void**>(&E->h_f64), 8 * sizeof(double)) != cudaSuccess) {
+      cudaMallocHost(reinterpret_cast<void**>(&E->h_i32), 3 * 64 * sizeof(int32_t)) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&E->h_f64), 3 * 64 * sizeof(double)) != cudaSuccess) {
     set_last_error("cgpt_create: CUDA stream / pinned host allocation failed (%s)",
                    cudaGetErrorString(cudaGetLastError()));
     cgpt_destroy(E);
@@ -1081,6 +1134,60 @@ int cgpt_certify(cgpt_handle E, const float* x, const cgpt_noise_spec* noise, in
   return 0;
 }
 
+// Smooth.certify of K images in shared passes: every pass holds this rank's next draws of ALL K images (K * per rows),
+// so the per-rank batch stays large when the draws of an image are sharded over many GPUs (BASELINE.json configs[2]:
+// 64 images, N = 1000, 8 GPUs -> 138 draws per rank and image).  Draw i of image k is Philox (seed, stream_id + k, i)
+// whatever K, batch size and world size are: per-image counts equal K separate cgpt_certify calls bit for bit.
+int cgpt_certify_batch(cgpt_handle E, const float* const* xs, int K, const cgpt_noise_spec* noise, int64_t n0, int64_t n,
+                       double alpha, int batch_size, int rank, int world, void* comm, int* out_labels, double* out_radii,
+                       double* out_detail, void* stream) {
+  CGPT_REQUIRE(E && xs && noise && out_labels && out_radii, "cgpt_certify_batch: null argument");
+  CGPT_REQUIRE(n0 > 0 && n > 0 && batch_size > 0 && world > 0 && rank >= 0 && rank < world, "cgpt_certify_batch: bad sizes");
+  CGPT_REQUIRE(K >= 1 && K <= E->max_images && K <= 64, "cgpt_certify_batch: %d images, the workspace serves %d (<= 64)", K,
+               E->max_images);
+  CGPT_TRY(check_ready(E, 1, true));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Buffers& b = E->b;
+  const int nc = E->c.num_classes;
+  const long long img_elems = 3LL * E->c.img_size * E->c.img_size;
+  CGPT_CHECK_CUDA(cudaMemsetAsync(b.counts, 0, static_cast<size_t>(K) * 2 * nc * 8, s));
+  CGPT_CHECK_CUDA(cudaMemsetAsync(b.invalid, 0, 4, s));
+  for (int k = 0; k < K; ++k) {
+    CGPT_REQUIRE(xs[k] != nullptr, "cgpt_certify_batch: image %d is null", k);
+    CGPT_CHECK_CUDA(cudaMemcpyAsync(b.x_static + k * img_elems, xs[k], img_elems * 4, cudaMemcpyDefault, s));
+  }
+  const long long num = n0 + n;
+  const long long lo = (num * rank) / world, hi = (num * (rank + 1)) / world;
+  if (batch_size > E->ws_B) batch_size = E->ws_B;
+  long long per_max = batch_size / K;
+  CGPT_REQUIRE(per_max >= 1, "cgpt_certify_batch: batch_size %d holds no draw of each of the %d images", batch_size, K);
+  const long long n_chunks = hi > lo ? (hi - lo + per_max - 1) / per_max : 0;
+  long long first = lo;
+  for (long long ci = 0; ci < n_chunks; ++ci) {
+    const int per = static_cast<int>((hi - first + (n_chunks - ci) - 1) / (n_chunks - ci));   // balanced, each <= per_max
+    CGPT_TRY(noisy_labels_images(E, noise, static_cast<uint64_t>(first), K, per, b.labels, s));
+    CGPT_TRY(label_hist_images(b.labels, K * per, per, first, n0, nc, b.counts, b.invalid, s));
+    first += per;
+  }
+  if (world > 1 && comm != nullptr)
+    CGPT_TRY(cgpt_allreduce_counts(reinterpret_cast<int64_t*>(b.counts), K * 2 * nc, comm, s));
+  const double* lut = (E->lut != nullptr && E->lut_n == n && E->lut_alpha == alpha) ? E->lut : nullptr;
+  CGPT_TRY(certify_tail_batch(b.counts, K, nc, n, alpha, noise->sigma, lut, b.tail_label, b.tail_stats, s));
+  CGPT_CHECK_CUDA(cudaMemcpyAsync(E->h_i32, b.tail_label, K * 3 * 4, cudaMemcpyDeviceToHost, s));
+  CGPT_CHECK_CUDA(cudaMemcpyAsync(E->h_f64, b.tail_stats, K * 3 * 8, cudaMemcpyDeviceToHost, s));
+  CGPT_CHECK_CUDA(cudaStreamSynchronize(s));   // the one device->host read of the call
+  for (int k = 0; k < K; ++k) {
+    out_labels[k] = E->h_i32[3 * k];
+    out_radii[k] = E->h_i32[3 * k] < 0 ? 0.0 : E->h_f64[3 * k];
+    if (out_detail) {
+      out_detail[3 * k] = static_cast<double>(E->h_i32[3 * k + 1]);
+      out_detail[3 * k + 1] = E->h_f64[3 * k + 1];
+      out_detail[3 * k + 2] = E->h_f64[3 * k + 2];
+    }
+  }
+  return 0;
+}
+
 int cgpt_set_radius_lut(cgpt_handle E, int64_t n, double alpha, const double* lut) {
   CGPT_REQUIRE(E != nullptr, "cgpt_set_radius_lut: null handle");
   CGPT_REQUIRE(lut == nullptr || (n > 0 && alpha > 0.0 && alpha < 1.0), "cgpt_set_radius_lut: bad (n, alpha)");
@@ -1121,6 +1228,16 @@ int cgpt_set_option(cgpt_handle E, const char* key, int value) {
   else if (!strcmp(key, "label_smoothing_permille")) {
     CGPT_REQUIRE(value >= 0 && value < 1000, "cgpt_set_option: label_smoothing_permille %d outside [0, 1000)", value);
     E->label_smoothing = static_cast<float>(value) / 1000.f;
+  }
+  else if (!strcmp(key, "max_images")) {
+    // images per pass of cgpt_certify_batch; changes the workspace layout: set it BEFORE cgpt_workspace_bytes / bind
+    CGPT_REQUIRE(value >= 1 && value <= 64, "cgpt_set_option: max_images %d outside [1, 64]", value);
+    if (value != E->max_images) {   // the layout changes: the caller must size and bind the workspace again
+      drop_graphs(E);
+      E->ws = nullptr;
+      E->ws_B = 0;
+      E->max_images = value;
+    }
   }
   else CGPT_REQUIRE(false, "cgpt_set_option: unknown key '%s'", key);
   return 0;

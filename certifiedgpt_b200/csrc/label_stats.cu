@@ -218,11 +218,16 @@ __global__ void __launch_bounds__(256) certify_tail_kernel(const long long* __re
                                                            const long long* __restrict__ counts_est,
                                                            int num_classes, long long n, double alpha,
                                                            double sigma, const double* __restrict__ lut,
-                                                           int* __restrict__ out_label,
+                                                           long long img_stride, int* __restrict__ out_label,
                                                            double* __restrict__ out_stats) {
   __shared__ double sh[8];
   __shared__ long long s_best[256];
   __shared__ int s_idx[256];
+  // one block per image: image k's count vectors are `img_stride` elements further on, its outputs 3 further on
+  counts_sel += blockIdx.x * img_stride;
+  counts_est += blockIdx.x * img_stride;
+  out_label += blockIdx.x * 3;
+  out_stats += blockIdx.x * 3;
   long long best = -1;
   int bi = 0x7fffffff;
   for (int c = threadIdx.x; c < num_classes; c += blockDim.x) {
@@ -362,8 +367,51 @@ int certify_tail(const long long* counts_sel, const long long* counts_est, int n
                  cudaStream_t stream) {
   CGPT_REQUIRE(num_classes > 0 && n > 0 && alpha > 0.0 && alpha < 1.0,
                "certify_tail: bad arguments classes=%d n=%lld alpha=%g", num_classes, n, alpha);
-  certify_tail_kernel<<<1, 256, 0, stream>>>(counts_sel, counts_est, num_classes, n, alpha, sigma, lut,
+  certify_tail_kernel<<<1, 256, 0, stream>>>(counts_sel, counts_est, num_classes, n, alpha, sigma, lut, 0,
                                              out_label, out_stats);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// K images at once: image k's selection / estimation vectors at counts + k * 2 * num_classes (+ num_classes),
+// out_label[3k..] / out_stats[3k..] as in certify_tail
+int certify_tail_batch(const long long* counts, int images, int num_classes, long long n, double alpha, double sigma,
+                       const double* lut, int* out_label, double* out_stats, cudaStream_t stream) {
+  CGPT_REQUIRE(images > 0 && num_classes > 0 && n > 0 && alpha > 0.0 && alpha < 1.0,
+               "certify_tail_batch: bad arguments images=%d classes=%d n=%lld alpha=%g", images, num_classes, n, alpha);
+  certify_tail_kernel<<<images, 256, 0, stream>>>(counts, counts + num_classes, num_classes, n, alpha, sigma, lut,
+                                                  2LL * num_classes, out_label, out_stats);
+  CGPT_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// labels of a multi-image pass: row r belongs to image r / per_image and is global sample first + r % per_image of it;
+// samples below `boundary` are counted into the image's selection vector, the others into its estimation vector
+__global__ void __launch_bounds__(256) label_hist_images_kernel(const int* __restrict__ labels, int rows, int per_image,
+                                                                long long first, long long boundary, int num_classes,
+                                                                unsigned long long* __restrict__ counts,
+                                                                int* __restrict__ invalid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const int label = labels[i];
+  if (label < 0 || label >= num_classes) {
+    if (invalid) atomicAdd(invalid, 1);
+    return;
+  }
+  const int img = i / per_image;
+  const long long sample = first + (i - img * per_image);
+  const int vec = (boundary >= 0 && sample >= boundary) ? 1 : 0;
+  atomicAdd(&counts[(static_cast<long long>(img) * 2 + vec) * num_classes + label], 1ull);
+}
+
+int label_hist_images(const int* labels, int rows, int per_image, long long first, long long boundary, int num_classes,
+                      long long* counts, int* invalid, cudaStream_t stream) {
+  CGPT_REQUIRE(rows > 0 && per_image > 0 && rows % per_image == 0 && num_classes > 0,
+               "label_hist_images: bad shape rows=%d per_image=%d", rows, per_image);
+  label_hist_images_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(labels, rows, per_image, first, boundary, num_classes,
+                                                                  reinterpret_cast<unsigned long long*>(counts), invalid);
   CGPT_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -35,6 +35,10 @@ int label_hist(const int* labels, int B, int num_classes, long long* counts, int
 int certify_tail(const long long* counts_sel, const long long* counts_est, int num_classes, long long n,
                  double alpha, double sigma, const double* lut, int* out_label, double* out_stats,
                  cudaStream_t stream);
+int certify_tail_batch(const long long* counts, int images, int num_classes, long long n, double alpha, double sigma,
+                       const double* lut, int* out_label, double* out_stats, cudaStream_t stream);
+int label_hist_images(const int* labels, int rows, int per_image, long long first, long long boundary, int num_classes,
+                      long long* counts, int* invalid, cudaStream_t stream);
 int predict_tail(const long long* counts, int num_classes, double alpha, int* out_label,
                  double* out_stats, cudaStream_t stream);
 int ce_loss(const float* logits, long long ld, int rows, int cols, const int* targets, float* token_loss,

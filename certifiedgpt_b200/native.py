@@ -67,6 +67,7 @@ def _declare(lib):
                          C.POINTER(f64), vp],
         "cgpt_predict": [vp, vp, pns, i64, f64, i32, i32, i32, vp, C.POINTER(i32), C.POINTER(f64), vp],
         "cgpt_set_radius_lut": [vp, i64, f64, vp],
+        "cgpt_certify_batch": [vp, vp, i32, pns, i64, i64, f64, i32, i32, i32, vp, vp, vp, vp, vp],
         "cgpt_last_counts": [vp, C.POINTER(vp)],
         "cgpt_last_decode_steps": [vp],
         "cgpt_set_option": [vp, C.c_char_p, i32],
@@ -190,16 +191,19 @@ class NativeMiniGPT4Engine:
         self._ws = None
         self._ws_B = 0
         self._ws_encoder_only = False
+        self._images = 1
         self._comm = None
         self.last_steps = 0
         if max_batch:
             self.reserve(max_batch)
 
     @classmethod
-    def from_engine(cls, eng: MiniGPT4Engine, *, early_exit=None, use_graphs=True, max_batch=0):
-        """Native engine over the packed weights of an existing Python engine (no second copy)."""
+    def from_engine(cls, eng: MiniGPT4Engine, *, early_exit=None, use_graphs=True, max_batch=0, max_new_tokens=None):
+        """Native engine over the packed weights of an existing Python engine (no second copy).  max_new_tokens may be
+        lowered below the source engine's (its rotary tables cover every shorter budget)."""
+        assert max_new_tokens is None or 1 <= max_new_tokens <= eng.max_new_tokens
         return cls(eng.cfg, None, eng.prefix_ids, eng.suffix_ids, None, eng.num_classes,
-                   max_new_tokens=eng.max_new_tokens, min_length=eng.min_length, device=eng.dev,
+                   max_new_tokens=max_new_tokens or eng.max_new_tokens, min_length=eng.min_length, device=eng.dev,
                    early_exit=eng.early_exit if early_exit is None else early_exit, use_graphs=use_graphs,
                    max_batch=max_batch, _packed_from=eng)
 
@@ -214,6 +218,12 @@ class NativeMiniGPT4Engine:
     def eval(self):
         return self
 
+    def set_answer_table(self, answer_table):
+        """Replace the answer vocabulary: iterable of (token id sequence, class id); unknown answers -> num_classes - 1."""
+        self.table_keys, self.table_vals = L.build_answer_table(answer_table, self.cfg.llm.eos_id, self.dev)
+        L.check(self._lib.cgpt_set_answer_table(self._h, L.ptr(self.table_keys), L.ptr(self.table_vals),
+                                                self.table_keys.numel()))
+
     def set_option(self, key, value):
         """run-time switches of the handle: "use_graphs", "early_exit"."""
         L.check(self._lib.cgpt_set_option(self._h, key.encode(), int(value)))
@@ -224,10 +234,16 @@ class NativeMiniGPT4Engine:
         L.check(self._lib.cgpt_workspace_bytes(self._h, int(B), int(encoder_only), C.byref(n)))
         return n.value
 
-    def reserve(self, B, encoder_only=False):
-        """Make sure the workspace serves batches of B samples (re-binding drops the captured graphs)."""
-        if self._ws is not None and B <= self._ws_B and (self._ws_encoder_only == encoder_only or not self._ws_encoder_only):
+    def reserve(self, B, encoder_only=False, images=1):
+        """Make sure the workspace serves batches of B samples, drawn from up to `images` images per pass
+        (re-binding drops the captured graphs)."""
+        if (self._ws is not None and B <= self._ws_B and images <= self._images
+                and (self._ws_encoder_only == encoder_only or not self._ws_encoder_only)):
             return
+        if images > self._images:
+            self.set_option("max_images", images)      # changes the layout: unbinds the workspace
+            self._images, self._ws, self._ws_B = int(images), None, 0
+            B = max(B, 1)
         need = self.workspace_bytes(B, encoder_only)
         self._ws = None
         torch.cuda.empty_cache()
@@ -338,6 +354,35 @@ class NativeMiniGPT4Engine:
         counts = self._last_counts()
         return label.value, radius.value, {"cAHat": int(detail[0]), "pABar": detail[1], "nA": int(detail[2]),
                                            "counts_selection": counts[0], "counts_estimation": counts[1]}
+
+    @torch.no_grad()
+    def certify_batch(self, xs, n0, n, alpha, batch_size, sigma, *, seed=0, stream_id=0, noise_space=L.SPACE_NORMALIZED,
+                      noise_kind=L.NOISE_GAUSSIAN, mean=L.BLIP_MEAN, std=L.BLIP_STD, process_group=None, exact_tail=True):
+        """Smooth.certify of K images in shared passes (cgpt_certify_batch): every pass holds this rank's next draws
+        of ALL K images.  xs: list of [3,S,S] fp32 tensors (host or device); image k uses Philox stream stream_id + k.
+        Returns a list of K (label or -1, radius, detail dict); per image bit-identical to `certify`."""
+        K = len(xs)
+        assert 1 <= K <= 64
+        for x in xs:
+            self._check_x(x)
+        rank, world, comm = self._comm_for(process_group)
+        per_rank = -(-int(n0 + n) // world)
+        self.reserve(min(int(batch_size), K * per_rank), images=K)
+        spec = self._spec(sigma, seed, stream_id, noise_space, noise_kind, mean, std, None, 0)
+        self._lut = L.radius_lut(n, alpha, self.dev) if exact_tail else None
+        L.check(self._lib.cgpt_set_radius_lut(self._h, int(n), float(alpha), L.ptr(self._lut)))
+        ptrs = (C.c_void_p * K)(*[x.data_ptr() for x in xs])
+        labels, radii, detail = (C.c_int * K)(), (C.c_double * K)(), (C.c_double * (3 * K))()
+        with torch.cuda.device(self.dev):
+            L.check(self._lib.cgpt_certify_batch(self._h, ptrs, K, C.byref(spec), int(n0), int(n), float(alpha),
+                                                 int(batch_size), rank, world, comm, labels, radii, detail, L.stream_ptr()))
+        self.last_steps = self._lib.cgpt_last_decode_steps(self._h)
+        p = C.c_void_p()
+        L.check(self._lib.cgpt_last_counts(self._h, C.byref(p)))
+        counts = self._ws_view(p.value, K * 2 * self.num_classes * 8).view(torch.int64).view(K, 2, self.num_classes).clone()
+        return [(labels[k], radii[k], {"cAHat": int(detail[3 * k]), "pABar": detail[3 * k + 1], "nA": int(detail[3 * k + 2]),
+                                       "counts_selection": counts[k, 0], "counts_estimation": counts[k, 1]})
+                for k in range(K)]
 
     @torch.no_grad()
     def predict(self, x, n, alpha, batch_size, sigma, *, eps=None, seed=0, stream_id=0,

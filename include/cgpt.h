@@ -353,6 +353,16 @@ int cgpt_sample_noise(cgpt_handle h, const float* x, const cgpt_noise_spec* nois
 int cgpt_certify(cgpt_handle h, const float* x, const cgpt_noise_spec* noise, int64_t n0, int64_t n, double alpha,
                  int batch_size, int rank, int world, void* comm, int* out_label, double* out_radius,
                  double* out_detail, void* stream);
+/* Smooth.certify of K images in shared passes (BASELINE.json configs[2]: a 64-image subset whose draws are sharded over
+ * 8 GPUs): every pass holds this rank's next draws of ALL K images, so the per-rank batch stays large (8 images x 138 draws
+ * instead of 138).  xs: host array of K pointers to fp32 [3,S,S] images (host or device memory).  Image k is drawn from
+ * Philox stream noise->stream_id + k, draw i = global sample index i: per-image counts, labels and radii equal K separate
+ * cgpt_certify calls bit for bit, whatever K, batch_size and world are.  One all-reduce of K * 2 * num_classes int64
+ * counts, K tails on the device, one D2H read.  Needs cgpt_set_option(h, "max_images", >= K) before the workspace is bound.
+ * out_labels / out_radii: host [K]; out_detail (host, nullable): [K][3] = {cAHat, pABar, nA}. */
+int cgpt_certify_batch(cgpt_handle h, const float* const* xs, int K, const cgpt_noise_spec* noise, int64_t n0, int64_t n,
+                       double alpha, int batch_size, int rank, int world, void* comm, int* out_labels, double* out_radii,
+                       double* out_detail, void* stream);
 /* Bind the (n, alpha) table of cgpt_certify_tail_lut to the handle (caller-owned device memory, like the weights;
  * NULL unbinds): cgpt_certify calls with exactly this n and alpha take pABar / radius from it (bit-identical to the
  * reference's SciPy tail), every other call uses the device bisection. */
@@ -366,7 +376,8 @@ int cgpt_last_counts(cgpt_handle h, const int64_t** counts);
 /* decode steps run by the last batch (< max_new_tokens when early_exit stopped the loop), or -1 */
 int cgpt_last_decode_steps(cgpt_handle h);
 /* run-time switches: "use_graphs" (0 = launch every kernel eagerly, e.g. for per-kernel timing),
- * "early_exit", "label_smoothing_permille" (cgpt_lm_loss: 100 = the reference's label_smoothing=0.1) */
+ * "early_exit", "label_smoothing_permille" (cgpt_lm_loss: 100 = the reference's label_smoothing=0.1),
+ * "max_images" (images per pass of cgpt_certify_batch; changing it unbinds the workspace: size and bind it again) */
 int cgpt_set_option(cgpt_handle h, const char* key, int value);
 
 /* ---------------------------------------------------------------- the one collective on the path

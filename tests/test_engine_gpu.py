@@ -119,8 +119,9 @@ def test_smooth_certify_with_engine_matches_oracle(space):
     assert int(got_sel.sum()) == n0 and int(got_est.sum()) == n
     # per sample: the engine's label of every draw equals the oracle's wherever the oracle's top-2 margin is safe
     kw = dict(noise_space=L.SPACE_PIXEL, mean=L.BLIP_MEAN, std=L.BLIP_STD) if space == "pixel" else {}
-    lab = torch.cat([eng.noisy_labels(x.cuda(), min(50, n0 + n - f), sigma, eps=eps[f:f + 50].cuda(), first_sample=f, **kw)
-                     for f in range(0, n0 + n, 50)]).cpu().long()
+    # (.clone(): the Python engine returns a view of its label buffer, which the next call overwrites)
+    lab = torch.cat([eng.noisy_labels(x.cuda(), min(50, n0 + n - f), sigma, eps=eps[f:f + 50].cuda(), first_sample=f,
+                                      **kw).clone() for f in range(0, n0 + n, 50)]).cpu().long()
     assert torch.equal(torch.bincount(lab[:n0], minlength=6), got_sel)      # counts = histogram of per-sample labels
     assert torch.equal(torch.bincount(lab[n0:], minlength=6), got_est)
     ref, margins = [], []

@@ -386,3 +386,30 @@ def test_empty_and_single_draw_calls():
         rc = nat._lib.cgpt_sample_noise(nat._h, C.c_void_p(x.data_ptr()), C.byref(spec), 0, num, bs, split, rank, world,
                                         None, L.ptr(counts), None, L.stream_ptr())
         assert rc != 0 and nat._lib.cgpt_last_error()
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_certify_batch_equals_one_image_at_a_time(use_graphs):
+    """cgpt_certify_batch: K images share every pass; per image the counts, label and radius of K successive
+    Smooth.certify calls, bit for bit, whatever the batch size (image k is drawn from Philox stream image_id + k)."""
+    from certifiedgpt_b200.randomized_smoothing.smoothing import Smooth
+    cfg, n_classes = WIDE, 8
+    sd, py, nat, _ = _setup(cfg, seed=31, max_new=2, n_classes=n_classes, use_graphs=use_graphs, all_pairs=True)
+    S = cfg.vit.img_size
+    xs = [torch.rand(3, S, S, generator=torch.Generator().manual_seed(50 + i)) for i in range(5)]
+    n0, n, sigma, alpha = 20, 90, 0.5, 0.001
+    one = Smooth(nat, n_classes, sigma, seed=9)
+    want, want_counts = [], []
+    for x in xs:
+        want.append(one.certify(x.cuda(), n0, n, alpha, 64))
+        want_counts.append((one.last_counts_selection.clone(), one.last_counts_estimation.clone()))
+    for bs, host in ((550, False), (64, True), (7, False)):     # 110, 12 and 1 draw(s) of each image per pass
+        many = Smooth(nat, n_classes, sigma, seed=9)
+        got = many.certify_batch([x if host else x.cuda() for x in xs], n0, n, alpha, bs)
+        assert got == want, bs
+        for d, (sel, est) in zip(many.last_batch_detail, want_counts):
+            assert torch.equal(d["counts_selection"], sel) and torch.equal(d["counts_estimation"], est)
+            assert int(d["counts_selection"].sum()) == n0 and int(d["counts_estimation"].sum()) == n
+        assert many.image_id == len(xs)
+    # the histograms are not degenerate: the images do not all land in one class
+    assert len({int(c[1].argmax()) for c in want_counts}) + sum(int((c[1] > 0).sum()) > 1 for c in want_counts) > 1
