@@ -40,6 +40,9 @@ class MiniGPT4CertifyAgent:
                 break
             item = self.dataset[i]
             x, label = item["image"], int(item["label"])
+            # every item has its own question (vqav2_dataset.py:19-166): the label answers THAT question
+            if item.get("suffix_ids") is not None:
+                self.smooth.base_classifier.set_question(item["suffix_ids"])
             self.smooth.image_id = i           # Philox stream = dataset index: results do not depend on order
             before = time.time()
             prediction, radius = self.smooth.certify(x.cuda(non_blocking=True), self.n0, self.n, self.alpha,

@@ -4,8 +4,15 @@
 Same loop as the reference, minus the TPU / wandb / checkpoint plumbing (out of scope): per epoch
 `train` (maybe_add_noise -> forward -> backward -> reduce + AdamW -> lr_scheduler.step, :149-195) then `eval`
 (validation loss under no_grad, :197-230), best-loss tracking with patience (:104-114), loss history (:121).
-A dataset item is {"image": [3,S,S] fp32, "answer_ids": list[int]} (the answer text already tokenised with the
-Llama tokenizer and terminated by the end symbol, minigpt_base.py:297-311); batches are padded with -100.
+A dataset item is {"image": [3,S,S] fp32, "answer_ids": list[int], "suffix_ids": list[int] (optional)}: the answer
+text already tokenised with the Llama tokenizer and terminated by the end symbol (minigpt_base.py:297-311), and the
+item's OWN instruction as the token ids after <ImageHere> (data/vqav2.py::finetune_items) - every sample is trained on
+its instruction_input, as MiniGPTBase.forward does.  Answers are padded with -100; a batch holds items whose
+instructions have the same token length (bucketing inside the epoch's shuffled order), so no prompt padding exists.
+Data parallelism (DistributedSampler(shuffle=True) in the reference): every epoch's order is a seeded permutation, rank r
+of W takes batches r, r + W, ... and draws its noise from its own Philox sample range; the gradient all-reduce then
+averages DIFFERENT batches.  The learning rate of a step is the one the scheduler set AFTER the previous optimizer step
+(lr_scheduler.step(epoch, step) follows optimizer_step in the reference): the first step runs at init_lr.
 """
 import math
 
@@ -25,11 +32,19 @@ def linear_warmup_cosine_lr(cur_epoch, cur_step, *, max_epoch, iters_per_epoch, 
 
 
 def collate(items, pad=-100):
+    """-> (images [B,3,S,S], answers [B,na] padded with -100, suffix ids [B,ns] or None)."""
     na = max(len(it["answer_ids"]) for it in items)
     ans = torch.full((len(items), na), pad, dtype=torch.long)
     for i, it in enumerate(items):
         ans[i, :len(it["answer_ids"])] = torch.as_tensor(it["answer_ids"], dtype=torch.long)
-    return torch.stack([it["image"] for it in items]).float(), ans
+    sfx = None
+    if all(it.get("suffix_ids") is not None for it in items):
+        lens = {len(it["suffix_ids"]) for it in items}
+        assert len(lens) == 1, "a batch must hold instructions of one token length (the agent buckets by length)"
+        sfx = torch.tensor([list(it["suffix_ids"]) for it in items], dtype=torch.int32)
+    else:
+        assert all(it.get("suffix_ids") is None for it in items), "either every item carries suffix_ids or none does"
+    return torch.stack([it["image"] for it in items]).float(), ans, sfx
 
 
 class MiniGPT4FineTuneAgent:
@@ -46,6 +61,13 @@ class MiniGPT4FineTuneAgent:
         self.trainer = LlamaProjTrainer(engine, lr=init_lr, betas=(beta1, beta2), weight_decay=weight_decay,
                                         max_batch=batch_size, max_answer=max_answer, process_group=process_group)
         self.patience, self.seed = patience, seed
+        self.process_group = process_group
+        self.rank, self.world = 0, 1
+        if process_group is not None:
+            import torch.distributed as dist
+            g = None if process_group is True else process_group
+            self.rank, self.world = dist.get_rank(g), dist.get_world_size(g)
+        self._prev_lr = init_lr       # AdamW is built with lr = init_lr (create_optimizer :338-347)
         self.loss_history = {"train_loss": [], "val_loss": [], "lr": []}
         self.best_val_loss, self.best_state = float("inf"), None
 
@@ -53,18 +75,41 @@ class MiniGPT4FineTuneAgent:
     def setup_agent(cls, **kwargs):
         return cls(**kwargs)
 
-    def _batches(self, ds):
-        n = len(ds) // self.batch_size * self.batch_size           # drop_last=True (:332)
-        for i in range(0, n, self.batch_size):
-            yield collate([ds[j] for j in range(i, i + self.batch_size)])
+    def _batch_indices(self, ds, epoch, shuffle):
+        """This rank's batches of the epoch, as index lists: a seeded permutation (train) or the dataset order (eval),
+        bucketed by instruction length so that a batch needs no prompt padding, full batches only (drop_last=True, :332),
+        dealt round-robin to the ranks."""
+        n = len(ds)
+        order = list(range(n))
+        if shuffle:
+            g = torch.Generator().manual_seed(self.seed * 1000003 + epoch)
+            order = torch.randperm(n, generator=g).tolist()
+        buckets, batches = {}, []
+        for j in order:
+            sfx = ds[j].get("suffix_ids")          # items are prepared dicts (data/vqav2.py::finetune_items)
+            key = len(sfx) if sfx is not None else -1
+            b = buckets.setdefault(key, [])
+            b.append(j)
+            if len(b) == self.batch_size:
+                batches.append(b)
+                buckets[key] = []
+        batches = batches[:len(batches) // self.world * self.world]       # every rank runs the same number of steps
+        return batches[self.rank::self.world]
+
+    def _batches(self, ds, epoch=0, shuffle=False):
+        for idx in self._batch_indices(ds, epoch, shuffle):
+            yield collate([ds[j] for j in idx])
 
     def train(self, epoch):
-        total, nb, lr = 0.0, 0, self.trainer.lr
-        for step, (images, answers) in enumerate(self._batches(self.train_set)):
-            lr = linear_warmup_cosine_lr(epoch, step, **self.sched)
+        total, nb, lr = 0.0, 0, self._prev_lr
+        for step, (images, answers, sfx) in enumerate(self._batches(self.train_set, epoch, shuffle=True)):
+            # the reference calls lr_scheduler.step(epoch, step) AFTER optimizer_step (:176-178): this step runs at the
+            # rate set after the previous one, the very first at AdamW's init_lr
+            lr = self._prev_lr
             gstep = epoch * self.sched["iters_per_epoch"] + step    # Philox stream of the uniform noise
             loss = self.trainer.train_step(images.to(self.engine.dev), answers, self.noise_level, seed=self.seed, step=gstep,
-                                           lr=lr)
+                                           lr=lr, suffix_ids=sfx, sample_offset=self.rank * self.batch_size)
+            self._prev_lr = linear_warmup_cosine_lr(epoch, step, **self.sched)
             total += float(loss.item())
             nb += 1
         self.loss_history["lr"].append(lr)
@@ -76,11 +121,11 @@ class MiniGPT4FineTuneAgent:
             return float("inf")
         total, nb = 0.0, 0
         nval = max(1, len(self.val_set) // self.batch_size)
-        for i, (images, answers) in enumerate(self._batches(self.val_set)):
+        for i, (images, answers, sfx) in enumerate(self._batches(self.val_set)):
             # the reference's validation loop noises its inputs too (maybe_add_noise, :209); its own Philox streams
             step = (1 << 30) + epoch * nval + i
             total += float(self.trainer.forward(images.to(self.engine.dev), answers, self.noise_level, seed=self.seed,
-                                                step=step).item())
+                                                step=step, suffix_ids=sfx, sample_offset=self.rank * self.batch_size).item())
             nb += 1
         return total / nb if nb else float("inf")
 

@@ -38,6 +38,9 @@ class MiniGPT4PredictAgent:
                 break
             item = self.dataset[i]
             x, label = item["image"], int(item["label"])
+            # every item has its own question (vqav2_dataset.py:19-166): the label answers THAT question
+            if item.get("suffix_ids") is not None:
+                self.smooth.base_classifier.set_question(item["suffix_ids"])
             self.smooth.image_id = i
             before = time.time()
             prediction = self.smooth.predict(x.cuda(non_blocking=True), self.n, self.alpha, self.batch_size)

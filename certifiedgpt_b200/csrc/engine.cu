@@ -123,6 +123,8 @@ struct Buffers {   // all inside the caller's workspace
 
 struct GraphSet {
   int B, K, space, kind;   // K = images per pass (B / K draws of each)
+  int ns;                  // question length and ids buffer the graphs were captured with (cgpt_set_question)
+  const void* suffix;
   float mean[3], std[3];
   cudaGraphExec_t g0 = nullptr;
   std::vector<cudaGraphExec_t> steps;
@@ -145,7 +147,8 @@ struct cgpt_engine {
   bool resolved = false;
   // derived sizes
   int T = 0, Pn = 0, G = 0, vhd = 0, qhd = 0, lhd = 0, n_cross = 0;
-  int P = 0, ns = 0, Tp = 0, cache_rows = 0;
+  int P = 0, ns = 0, Tp = 0, cache_rows = 0;   // ns / Tp: the CURRENT question (cgpt_set_question), <= the config's maximum
+  int Tp_max = 0;                              // qf_queries + cfg.n_suffix: what the workspace and the KV cache are sized for
   // resolved weights
   const void *patch_w = nullptr, *qf_q0 = nullptr, *ckv_w = nullptr, *proj_w = nullptr, *emb = nullptr,
              *head_w = nullptr;
@@ -314,8 +317,8 @@ int resolve(Engine* E) {
     auto it = E->w.find("rope.cos");
     CGPT_REQUIRE(it != E->w.end() && E->w.count("rope.sin"), "engine: rope.cos / rope.sin are not bound");
     CGPT_REQUIRE(it->second.dtype == CGPT_DT_F32 && it->second.cols == E->lhd / 2 &&
-                     it->second.rows >= E->P + E->Tp + c.max_new_tokens,
-                 "engine: rope tables must be f32 [>= %d, %d]", E->P + E->Tp + c.max_new_tokens, E->lhd / 2);
+                     it->second.rows >= E->P + E->Tp_max + c.max_new_tokens,
+                 "engine: rope tables must be f32 [>= %d, %d]", E->P + E->Tp_max + c.max_new_tokens, E->lhd / 2);
     E->rope_cos = static_cast<const float*>(it->second.p);
     E->rope_sin = static_cast<const float*>(E->w["rope.sin"].p);
   }
@@ -334,7 +337,7 @@ long long layout(Engine* E, int B, bool encoder_only, char* base, Buffers* out) 
     return p;
   };
   const long long Mv = static_cast<long long>(B) * E->T, Mq = static_cast<long long>(B) * c.qf_queries,
-                  Ml = static_cast<long long>(B) * E->Tp;
+                  Ml = static_cast<long long>(B) * E->Tp_max;
   const long long D = c.vit_dim, Hq = c.qf_hidden, Hl = c.llm_hidden;
   Buffers b;
   memset(&b, 0, sizeof(b));
@@ -703,7 +706,7 @@ int noise_segments(Engine* E, const cgpt_noise_spec* n, int B, int K, cudaStream
 
 int get_graphs(Engine* E, const cgpt_noise_spec* n, int B, int K, cudaStream_t s, GraphSet** out) {
   for (auto& g : E->graphs)
-    if (g.B == B && g.K == K && g.space == n->noise_space && g.kind == n->noise_kind && !memcmp(g.mean, n->mean, 12) &&
+    if (g.B == B && g.K == K && g.ns == E->ns && g.suffix == E->suffix_ids && g.space == n->noise_space && g.kind == n->noise_kind && !memcmp(g.mean, n->mean, 12) &&
         !memcmp(g.std, n->std, 12)) {
       *out = &g;
       return 0;
@@ -719,6 +722,7 @@ int get_graphs(Engine* E, const cgpt_noise_spec* n, int B, int K, cudaStream_t s
 
   GraphSet gs;
   gs.B = B; gs.K = K; gs.space = n->noise_space; gs.kind = n->noise_kind;
+  gs.ns = E->ns; gs.suffix = E->suffix_ids;
   memcpy(gs.mean, n->mean, 12);
   memcpy(gs.std, n->std, 12);
   cudaStream_t cs = E->cap_stream;
@@ -937,7 +941,8 @@ int cgpt_create(const cgpt_model_config* cfg, cgpt_handle* out) {
   E->P = c.n_prefix;
   E->ns = c.n_suffix;
   E->Tp = c.qf_queries + c.n_suffix;
-  E->cache_rows = E->P + E->Tp + c.max_new_tokens;
+  E->Tp_max = E->Tp;
+  E->cache_rows = E->P + E->Tp_max + c.max_new_tokens;
   if (cudaStreamCreateWithFlags(&E->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&E->h_i32), 3 * 64 * sizeof(int32_t)) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&E->h_f64), 3 * 64 * sizeof(double)) != cudaSuccess) {
@@ -978,6 +983,19 @@ int cgpt_set_prompt(cgpt_handle E, const int32_t* prefix_ids, const int32_t* suf
   E->suffix_ids = suffix_ids;
   E->prompt_set = true;
   drop_graphs(E);
+  return 0;
+}
+
+int cgpt_set_question(cgpt_handle E, const int32_t* suffix_ids, int n_suffix) {
+  CGPT_REQUIRE(E != nullptr, "cgpt_set_question: null handle");
+  CGPT_REQUIRE(n_suffix >= 0 && n_suffix <= E->c.n_suffix, "cgpt_set_question: %d question tokens, the handle was created for <= %d",
+               n_suffix, E->c.n_suffix);
+  CGPT_REQUIRE(n_suffix == 0 || suffix_ids != nullptr, "cgpt_set_question: null ids");
+  // graphs are keyed by (question length, ids buffer): a caller that rewrites ONE device buffer in place replays the
+  // graphs captured for that length, a new buffer or length captures its own set
+  E->suffix_ids = suffix_ids;
+  E->ns = n_suffix;
+  E->Tp = E->c.qf_queries + n_suffix;
   return 0;
 }
 

@@ -132,7 +132,9 @@ __device__ __forceinline__ void load_resid16(const EpiParams& p, long long out_r
   }
 }
 
-// process 16 consecutive accumulator columns of one row and store them
+// process 16 consecutive accumulator columns of one row and store them (HM: head-major q|k|v scatter, its own kernel
+// instantiation so that the hot epilogue loop of every other GEMM keeps its code size)
+template <bool HM>
 __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiParams& p, const float* bias_s,
                                                  const float* resid_r, int m, long long out_row, int n0) {
   constexpr int NC = 16;
@@ -189,7 +191,7 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
 #pragma unroll
     for (int i = 0; i < NC; ++i) v[i] += resid_r[i];
   }
-  if (p.hm_T > 0) {
+  if constexpr (HM) {
     // 8-element pieces never straddle a head (hd % 8 == 0); which / h / d are the same for the whole warp
 #pragma unroll
     for (int i = 0; i < NC; i += 8) {
@@ -227,6 +229,7 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
 // chunk and its residual prefetch are in flight while the current chunk is processed; the loop is
 // unrolled by exactly 2 (static register double buffer) and NOT further, so the SASS stays small
 // enough for the instruction cache with 8 warps running it.
+template <bool HM>
 __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams& epi, const float* bias_s,
                                                 int m, long long out_row, bool row_ok, int n_base, int N,
                                                 int c0, int c1) {
@@ -242,7 +245,7 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams&
       tmem_ld_x16(t_row + (c + 1) * 16, r1);
       if (has_res && n_base + (c + 1) * 16 < N) load_resid16(epi, out_row, n_base + (c + 1) * 16, rr1);
     }
-    if (row_ok && n_base + c * 16 < N) epilogue_store16(r0, epi, bias_s + c * 16, rr0, m, out_row, n_base + c * 16);
+    if (row_ok && n_base + c * 16 < N) epilogue_store16<HM>(r0, epi, bias_s + c * 16, rr0, m, out_row, n_base + c * 16);
     if (c + 1 < c1) {
       tmem_ld_wait();
       if (c + 2 < c1) {
@@ -250,7 +253,7 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams&
         if (has_res && n_base + (c + 2) * 16 < N) load_resid16(epi, out_row, n_base + (c + 2) * 16, rr0);
       }
       if (row_ok && n_base + (c + 1) * 16 < N)
-        epilogue_store16(r1, epi, bias_s + (c + 1) * 16, rr1, m, out_row, n_base + (c + 1) * 16);
+        epilogue_store16<HM>(r1, epi, bias_s + (c + 1) * 16, rr1, m, out_row, n_base + (c + 1) * 16);
     }
   }
 }
@@ -405,7 +408,12 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
   n = r / gm;
 }
 
-template <int BN, int CTAS, bool ROPE = false>
+// MODE: 0 = the common epilogues, 1 = fused rotary + KV-cache append (ROPE), 2 = head-major q|k|v scatter
+//       3 = in-place fp32 residual update as a coalesced load + add + store (the short-K ViT proj GEMM)
+// Each special epilogue is its own instantiation so that the hot epilogue loop of the common kernel keeps the code size
+// it was tuned at (the GELU GEMM lost 19 % when two more branches were compiled into it: instruction cache).
+constexpr int MODE_PLAIN = 0, MODE_ROPE = 1, MODE_HM = 2, MODE_RMW = 3;
+template <int BN, int CTAS, int MODE = MODE_PLAIN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
@@ -589,24 +597,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       if (epi.row_period > 0 && epi.remap_stride > 0)
         out_row = (long long)(m / epi.row_period) * epi.remap_stride + epi.remap_offset +
                   (m % epi.row_period);
-      if (epi.hm_T > 0) {
+      if constexpr (MODE == MODE_HM) {
         // head-major: element offset of (sample b, head 0, token t, d 0) inside one of the q / k / v blocks
         const int b = m / epi.hm_T, t = m - b * epi.hm_T;
         out_row = (static_cast<long long>(b) * epi.hm_H * epi.hm_T + t) * epi.hm_hd;
       }
       const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-      if constexpr (ROPE) {
+      if constexpr (MODE == MODE_ROPE) {
         // BN = 256: this warp's half of the tile is one 128-wide head
         if (n_base + half * 128 < N) epilogue_rope_head(t_row + half * 128, epi, m, row_ok, n_base + half * 128);
+      } else if constexpr (MODE == MODE_RMW) {
+        epilogue_chunks_red<true>(t_row, epi, bias_s, red_stage + warp * (32 * 20), m_blk * BM + quarter * 32, M, n_base, N,
+                                  half == 0 ? 0 : NCH0, half == 0 ? NCH0 : NCH);
       } else if (epi.red_inplace == 2) {
         epilogue_chunks_red<false>(t_row, epi, bias_s, red_stage + warp * (32 * 20), m_blk * BM + quarter * 32, M, n_base, N,
                                    half == 0 ? 0 : NCH0, half == 0 ? NCH0 : NCH);
-      } else if (epi.red_inplace == 3) {
-        epilogue_chunks_red<true>(t_row, epi, bias_s, red_stage + warp * (32 * 20), m_blk * BM + quarter * 32, M, n_base, N,
-                                  half == 0 ? 0 : NCH0, half == 0 ? NCH0 : NCH);
       } else {
-        epilogue_chunks(t_row, epi, bias_s, m, out_row, row_ok, n_base, N, half == 0 ? 0 : NCH0,
-                        half == 0 ? NCH0 : NCH);
+        epilogue_chunks<MODE == MODE_HM>(t_row, epi, bias_s, m, out_row, row_ok, n_base, N, half == 0 ? 0 : NCH0,
+                                         half == 0 ? NCH0 : NCH);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -673,13 +681,13 @@ struct GemmProfRec { cudaEvent_t e0, e1; int M, N, K; };
 static std::deque<GemmProfRec> g_prof;
 static bool g_prof_on = false;
 
-template <int BN, int CTAS, bool ROPE = false>
+template <int BN, int CTAS, int MODE = MODE_PLAIN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                        const EpiParams& epi, int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTAS>;
   static bool configured = false;
   if (!configured) {
-    CGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS, ROPE>,
+    CGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
@@ -699,7 +707,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS, ROPE>, ta, tb, M, N, K, epi));
+  CGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS, MODE>, ta, tb, M, N, K, epi));
   ++g_gemm_launches;
   return 0;
 }
@@ -813,6 +821,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   if (bn == 0) bn = ctas == 2 ? (N > 176 ? 256 : (N > 128 ? 176 : 128)) : pick_bn(N);
   if ((force_bn & 0xfff) == 0 && rp == nullptr && e->max_ctas == 0) bn = pick_bn_skinny(M, N, ctas, bn, g_num_sms / ctas);
   if (rp != nullptr) bn = 256;   // the fused rotary epilogue needs one 128-wide head per epilogue warp
+  if (p.hm_T > 0) bn = 256;      // the head-major scatter lives in the 256-wide instantiations only
   {
     // Band height.  A weight that fits L2 several times over (ViT / Q-Former linears, <= 24 MB) stays resident
     // whatever the order, so a LOW band (4 m-tiles) is best: the n-tiles that share an A tile then run close
@@ -823,6 +832,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
     const long long w_bytes = static_cast<long long>(N) * K * 2;
     p.group_m = forced > 0 ? forced : (w_bytes <= (24LL << 20) ? 4 : GROUP_M_MAX);
   }
+  if (p.red_inplace == 3 && !(bn == 256 && ctas == 2 && rp == nullptr && p.hm_T == 0)) p.red_inplace = 2;   // RMW instantiation: CTA pairs, 256-wide tiles
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, A, M, K, lda, BM)) return rc;
   if (int rc = make_tmap(&tb, W, N, K, ldw, bn / ctas)) return rc;
@@ -841,8 +851,13 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   int rc = 0;
   if (rp != nullptr) {
     CGPT_REQUIRE(bn == 256, "gemm(rope): needs 256-wide N tiles (got %d)", bn);
-    rc = ctas == 2 ? launch_gemm<256, 2, true>(ta, tb, M, N, K, p, e->max_ctas, stream)
-                   : launch_gemm<256, 1, true>(ta, tb, M, N, K, p, e->max_ctas, stream);
+    rc = ctas == 2 ? launch_gemm<256, 2, MODE_ROPE>(ta, tb, M, N, K, p, e->max_ctas, stream)
+                   : launch_gemm<256, 1, MODE_ROPE>(ta, tb, M, N, K, p, e->max_ctas, stream);
+  } else if (p.hm_T > 0) {
+    rc = ctas == 2 ? launch_gemm<256, 2, MODE_HM>(ta, tb, M, N, K, p, e->max_ctas, stream)
+                   : launch_gemm<256, 1, MODE_HM>(ta, tb, M, N, K, p, e->max_ctas, stream);
+  } else if (p.red_inplace == 3) {
+    rc = launch_gemm<256, 2, MODE_RMW>(ta, tb, M, N, K, p, e->max_ctas, stream);
   } else
   switch (bn * 10 + ctas) {
     case 2561: rc = launch_gemm<256, 1>(ta, tb, M, N, K, p, e->max_ctas, stream); break;

@@ -179,23 +179,34 @@ def split_prompt(instruction_input, encode, bos_id=1, prompt_template=PROMPT_TEM
     return [bos_id] + [int(t) for t in encode(before)], [int(t) for t in encode(after)]
 
 
-def certify_items(dataset, vocabulary, indices=None):
-    """{"image", "label"} items for MiniGPT4CertifyAgent / MiniGPT4PredictAgent: label = class of the most probable
-    ground-truth answer under the answer vocabulary (certifiedgpt_b200.answers.AnswerVocabulary)."""
+def certify_items(dataset, vocabulary, indices=None, encode=None):
+    """{"image", "label"[, "prefix_ids", "suffix_ids"]} items for MiniGPT4CertifyAgent / MiniGPT4PredictAgent: label =
+    class of the most probable ground-truth answer under the answer vocabulary
+    (certifiedgpt_b200.answers.AnswerVocabulary).  With `encode` (the Llama tokenizer's text -> ids) every item carries
+    ITS question as token ids around <ImageHere>, in the evaluation call site's wording (`eval_prompt`): the agents hand
+    `suffix_ids` to engine.set_question before certifying the item, and the engine is built with the longest one.
+    Without `encode` the engine's fixed prompt is used - only meaningful when every item asks the same question."""
     out = []
     for i in (range(len(dataset)) if indices is None else indices):
         d = dataset.get_data(i)
         best = max(d["answer_weights"].items(), key=lambda kv: kv[1])[0] if d["answer_weights"] else d["answer"]
-        out.append({"image": d["image"], "label": vocabulary.label_of_text(best), "question_id": d["question_id"]})
+        item = {"image": d["image"], "label": vocabulary.label_of_text(best), "question_id": d["question_id"]}
+        if encode is not None:
+            question = EVAL_QUESTION_TEMPLATE.format(d["question"])
+            item["prefix_ids"], item["suffix_ids"] = split_prompt(eval_prompt(question), encode, prompt_template="{}")
+        out.append(item)
     return out
 
 
-def finetune_items(dataset, encode, indices=None, end_sym=END_SYM, max_txt_len=160):
-    """{"image", "answer_ids"} items for MiniGPT4FineTuneAgent: answer + end_sym tokenised without special tokens
-    (minigpt_base.py:297-311)."""
+def finetune_items(dataset, encode, indices=None, end_sym=END_SYM, max_txt_len=160, prompt_template=PROMPT_TEMPLATE):
+    """{"image", "answer_ids", "suffix_ids"} items for MiniGPT4FineTuneAgent: answer + end_sym tokenised without special
+    tokens (minigpt_base.py:297-311); suffix_ids = the item's own instruction as the token ids after <ImageHere>
+    (MiniGPTBase.forward trains every sample on ITS instruction_input, minigpt_base.py:323-362)."""
     out = []
     for i in (range(len(dataset)) if indices is None else indices):
         d = dataset[i]
+        prefix, suffix = split_prompt(d["instruction_input"], encode, prompt_template=prompt_template)
         out.append({"image": d["image"], "answer_ids": [int(t) for t in encode(d["answer"] + end_sym)][:max_txt_len],
-                    "question_id": d["question_id"], "instruction_input": d["instruction_input"]})
+                    "question_id": d["question_id"], "instruction_input": d["instruction_input"],
+                    "prefix_ids": prefix, "suffix_ids": suffix})
     return out

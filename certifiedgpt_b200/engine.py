@@ -53,6 +53,7 @@ class MiniGPT4Engine:
         self.P = len(self.prefix_ids)
         self.Tp = cfg.qf.n_query + len(self.suffix_ids)      # per-sample prompt rows
         self.S = self.P + self.Tp                            # full prompt length
+        self.Tp_max = self.Tp                                # the constructor's question is the LONGEST one (set_question)
         self.cache_rows = self.P + self.Tp + self.max_new_tokens   # [prefix | prompt rows | generated]
         self._pack(state_dict)
         self.table_keys, self.table_vals = L.build_answer_table(answer_table, cfg.llm.eos_id, self.dev)
@@ -71,6 +72,19 @@ class MiniGPT4Engine:
 
     def eval(self):
         return self
+
+    def set_question(self, suffix_ids):
+        """The question of the next calls: the token ids after the image ("</Img> {question} [/INST]",
+        minigpt_base.py:75-89), at most as many as the constructor's.  Every VQAv2 item has its own question
+        (vqav2_dataset.py:19-166); buffers and the KV cache keep the size of the longest one."""
+        ids = [int(i) for i in suffix_ids]
+        assert len(ids) <= self.Tp_max - self.cfg.qf.n_query, "question longer than the one the engine was built for"
+        self.suffix_ids = ids
+        self._suffix_buf[:len(ids)] = torch.tensor(ids, dtype=torch.int32, device=self.dev)
+        self.suffix_ids_dev = self._suffix_buf[:len(ids)]
+        self.Tp = self.cfg.qf.n_query + len(ids)
+        self.S = self.P + self.Tp
+        self._graphs = {}          # captured graphs hold the old prompt length
 
     # ------------------------------------------------------------------ weights
     def _pack(self, sd):
@@ -148,7 +162,8 @@ class MiniGPT4Engine:
         w["rope.cos"], w["rope.sin"] = _f32(fr.cos(), dev), _f32(fr.sin(), dev)
         self.w = w
         self.prefix_ids_dev = torch.tensor(self.prefix_ids, dtype=torch.int32, device=dev)
-        self.suffix_ids_dev = torch.tensor(self.suffix_ids, dtype=torch.int32, device=dev)
+        self._suffix_buf = torch.tensor(self.suffix_ids, dtype=torch.int32, device=dev)   # rewritten in place by set_question
+        self.suffix_ids_dev = self._suffix_buf
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, B):
@@ -157,7 +172,7 @@ class MiniGPT4Engine:
         cfg, dev = self.cfg, self.dev
         v, q, l = cfg.vit, cfg.qf, cfg.llm
         bf, f32 = torch.bfloat16, torch.float32
-        Mv, Mq, Ml = B * v.tokens, B * q.n_query, B * self.Tp
+        Mv, Mq, Ml = B * v.tokens, B * q.n_query, B * self.Tp_max
         n_cross = len(q.cross_layers())
 
         def e(*shape, dtype=bf):

@@ -55,6 +55,7 @@ def _declare(lib):
         "cgpt_bind_weight": [vp, C.c_char_p, vp, i64, i64, i32],
         "cgpt_set_prompt": [vp, vp, vp],
         "cgpt_set_answer_table": [vp, vp, vp, i32],
+        "cgpt_set_question": [vp, vp, i32],
         "cgpt_workspace_bytes": [vp, i32, i32, C.POINTER(i64)],
         "cgpt_bind_workspace": [vp, vp, i64, i32, i32, vp],
         "cgpt_vit_forward": [vp, vp, i32, vp, vp],
@@ -217,6 +218,21 @@ class NativeMiniGPT4Engine:
 
     def eval(self):
         return self
+
+    def set_question(self, suffix_ids):
+        """The question of the next calls (token ids after the image, at most as many as the constructor's): one device
+        buffer rewritten in place, so the graphs captured for a question length are replayed for every question of
+        that length (cgpt_set_question)."""
+        ids = [int(i) for i in suffix_ids]
+        src = self._src
+        if getattr(self, "_suffix_buf", None) is None:
+            self._suffix_buf = torch.zeros(max(1, src.Tp_max - self.cfg.qf.n_query), dtype=torch.int32, device=self.dev)
+        assert len(ids) <= self._suffix_buf.numel(), "question longer than the one the engine was built for"
+        if ids:
+            self._suffix_buf[:len(ids)] = torch.tensor(ids, dtype=torch.int32, device=self.dev)
+        L.check(self._lib.cgpt_set_question(self._h, L.ptr(self._suffix_buf), len(ids)))
+        self.Tp = self.cfg.qf.n_query + len(ids)
+        self.S = self.P + self.Tp
 
     def set_answer_table(self, answer_table):
         """Replace the answer vocabulary: iterable of (token id sequence, class id); unknown answers -> num_classes - 1."""

@@ -102,13 +102,25 @@ class LlamaProjTrainer:
     # ------------------------------------------------------------------ forward (activations kept)
     @torch.no_grad()
     def forward(self, images, answers, noise_level=0.0, *, seed=0, step=0, noise_kind=L.NOISE_UNIFORM,
-                noise_space=L.SPACE_NORMALIZED):
-        """images [B,3,S,S] fp32 CUDA, answers [B,na] int (-100 = padding) -> mean loss (device scalar)."""
+                noise_space=L.SPACE_NORMALIZED, suffix_ids=None, sample_offset=0):
+        """images [B,3,S,S] fp32 CUDA, answers [B,na] int (-100 = padding) -> mean loss (device scalar).
+        suffix_ids [B, ns] int (optional): every row's OWN instruction as the token ids after the image
+        (MiniGPTBase.forward trains each sample on its instruction_input, minigpt_base.py:323-362); rows of one batch
+        share the length ns <= the engine's (the agent buckets by length).  None: the engine's current question for
+        every row.  sample_offset: first Philox sample index of this batch (data-parallel ranks draw different noise)."""
         eng, cfg, w, buf = self.eng, self.cfg, self.w, self.buf
         v, q, l = cfg.vit, cfg.qf, cfg.llm
         B, na = answers.shape
         assert B <= self.max_batch and na <= self.max_answer and images.is_cuda
-        nq, ns, P, Hd, I = q.n_query, self.ns, self.P, l.hidden, l.inter
+        if suffix_ids is not None:
+            sfx = torch.as_tensor(suffix_ids).to(device=self.dev, dtype=torch.int32).contiguous()
+            assert sfx.dim() == 2 and sfx.shape[0] == B and sfx.shape[1] <= self.ns, "suffix_ids must be [B, ns <= engine's]"
+            assert int(sfx.min()) >= 0 and int(sfx.max()) < l.vocab, "suffix ids outside the vocabulary"
+            ns, sfx_ids, sfx_period = sfx.shape[1], sfx.view(-1), B * sfx.shape[1]
+        else:
+            ns, sfx_ids, sfx_period = len(eng.suffix_ids), eng.suffix_ids_dev, len(eng.suffix_ids)
+        assert int(torch.as_tensor(answers).max()) < l.vocab, "answer ids outside the vocabulary"
+        nq, P, Hd, I = q.n_query, self.P, l.hidden, l.inter
         Tl = nq + ns + na
         M = B * Tl
         lib = _lib()
@@ -116,15 +128,16 @@ class LlamaProjTrainer:
         eb = eng._encoder_buffers(B)
         G2 = v.grid * v.grid
         for b in range(B):
-            L.noise_patchify(images[b].float().contiguous(), 1, float(noise_level), seed=seed, stream_id=step, first_sample=b,
-                             noise_space=noise_space, noise_kind=noise_kind, out=eb["patches"][b * G2:(b + 1) * G2])
+            L.noise_patchify(images[b].float().contiguous(), 1, float(noise_level), seed=seed, stream_id=step,
+                             first_sample=sample_offset + b, noise_space=noise_space, noise_kind=noise_kind,
+                             out=eb["patches"][b * G2:(b + 1) * G2])
         qo = eng.qformer(B, eb, eng.vit_from_patches(B, eb))              # [B*nq, qf.hidden] bf16
         self.last_q = qo[:B * nq].clone()
         res, xn, qkv, act = (buf[k][:M] for k in ("res", "xn", "qkv", "act"))
         # llama_proj (trainable) into the image rows; suffix / answer embeddings behind it
         L.gemm(self.last_q, w["proj.w"], bias=w["proj.b"], out=res, row_period=nq, remap_stride=Tl, remap_offset=0)
         if ns > 0:
-            L.gather_rows(w["emb"], eng.suffix_ids_dev, B * ns, res, id_period=ns, remap=(ns, Tl, nq))
+            L.gather_rows(w["emb"], sfx_ids, B * ns, res, id_period=sfx_period, remap=(ns, Tl, nq))
         ans = answers.to(device=self.dev, dtype=torch.int32).contiguous()
         ans_in = torch.where(ans < 0, torch.full_like(ans, l.pad_id), ans).contiguous()
         L.gather_rows(w["emb"], ans_in.view(-1), B * na, res, id_period=B * na, remap=(na, Tl, nq + ns))
@@ -244,9 +257,10 @@ class LlamaProjTrainer:
                                          gscale, L.stream_ptr()))
         self.w["proj.b"].copy_(self.bp)                              # the GEMM epilogue reads the fp32 bias
 
-    def train_step(self, images, answers, noise_level, *, seed=0, step=0, lr=None):
+    def train_step(self, images, answers, noise_level, *, seed=0, step=0, lr=None, suffix_ids=None, sample_offset=0):
         """maybe_add_noise -> forward -> backward -> reduce + AdamW (agents/minigpt4_finetune_agent.py:165-181)."""
-        loss = self.forward(images, answers, noise_level, seed=seed, step=step)
+        loss = self.forward(images, answers, noise_level, seed=seed, step=step, suffix_ids=suffix_ids,
+                            sample_offset=sample_offset)
         self.backward()
         self.optimizer_step(lr)
         return loss

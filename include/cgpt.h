@@ -304,6 +304,12 @@ int cgpt_destroy(cgpt_handle h);
 /* Binds one packed tensor by name (device pointer, caller keeps it alive).  bf16 matrices are K-major
  * [out, in] (nn.Linear layout); names and packing: certifiedgpt_b200/engine.py::_pack. */
 int cgpt_bind_weight(cgpt_handle h, const char* name, const void* ptr, int64_t rows, int64_t cols, int dtype);
+/* The question of the NEXT calls (the tokens after the image: "</Img> {question} [/INST]", minigpt_base.py:75-89):
+ * n_suffix <= cgpt_model_config.n_suffix, which sizes the workspace and the KV cache (the maximum question length).
+ * suffix_ids: device int32 [n_suffix], caller-owned.  Every dataset item has its own question
+ * (datasets/datasets/vqav2_dataset.py:19-166): the certify / predict agents call this once per item.  Captured graphs
+ * are keyed by (n_suffix, suffix_ids): rewrite one device buffer in place to replay them. */
+int cgpt_set_question(cgpt_handle h, const int32_t* suffix_ids, int n_suffix);
 /* prompt token ids around the image (minigpt_base.py:75-89): device int32 arrays of n_prefix / n_suffix ids */
 int cgpt_set_prompt(cgpt_handle h, const int32_t* prefix_ids, const int32_t* suffix_ids);
 int cgpt_set_answer_table(cgpt_handle h, const uint64_t* table_keys, const int32_t* table_vals, int capacity);

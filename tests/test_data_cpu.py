@@ -72,6 +72,16 @@ def test_prompt_split_and_agent_items(fake_vqav2):
     assert [it["label"] for it in items] == [0, 1, 2]                    # "No." normalises to "no"
     ft = V.finetune_items(ds, enc)
     assert ft[1]["answer_ids"] == enc("no</s>") and ft[1]["image"].shape == (3, 56, 56)
+    # every item carries ITS question as the token ids around <ImageHere> (what the agents hand to set_question)
+    assert ft[1]["suffix_ids"] == V.split_prompt(ft[1]["instruction_input"], enc)[1] and ft[1]["prefix_ids"] == prefix
+    assert "is it raining" in ft[1]["instruction_input"] and ft[0]["suffix_ids"] != ft[1]["suffix_ids"]
+    with_q = V.certify_items(ds, vocab, encode=enc)
+    assert [it["label"] for it in with_q] == [0, 1, 2]
+    for it, d in zip(with_q, (ds.get_data(i) for i in range(len(ds)))):
+        want = V.split_prompt(V.eval_prompt(V.EVAL_QUESTION_TEMPLATE.format(d["question"])), enc, prompt_template="{}")
+        assert (it["prefix_ids"], it["suffix_ids"]) == want
+    assert len({tuple(it["suffix_ids"]) for it in with_q}) == len(with_q)    # different questions, different ids
+    assert len({tuple(it["prefix_ids"]) for it in with_q}) == 1             # one shared prefix (the engine's prefix KV)
 
 
 @pytest.mark.parametrize("size", [56, 224])

@@ -413,3 +413,30 @@ def test_certify_batch_equals_one_image_at_a_time(use_graphs):
         assert many.image_id == len(xs)
     # the histograms are not degenerate: the images do not all land in one class
     assert len({int(c[1].argmax()) for c in want_counts}) + sum(int((c[1] > 0).sum()) > 1 for c in want_counts) > 1
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_set_question_equals_an_engine_built_for_that_question(use_graphs):
+    """cgpt_set_question / MiniGPT4Engine.set_question: one engine, built for the longest question, answers every
+    (shorter or equal) question exactly as an engine constructed with that question does - ids, labels, decode steps."""
+    from certifiedgpt_b200.engine import MiniGPT4Engine
+    from certifiedgpt_b200.native import NativeMiniGPT4Engine
+    cfg = WIDE
+    long_q, short_q, other_q = (7, 8, 9, 10, 11, 12, 13), (20, 21, 22), (30, 31, 32, 33, 34, 35, 36)
+    sd, py, nat, _ = _setup(cfg, seed=23, max_new=2, suffix=long_q, use_graphs=use_graphs, all_pairs=True)
+    S = cfg.vit.img_size
+    x = torch.rand(3, S, S, generator=torch.Generator().manual_seed(3)).cuda()
+    want = {}
+    for q in (long_q, short_q, other_q):
+        ref = MiniGPT4Engine(cfg, sd, (1, 5, 6), q, [], 8, max_new_tokens=2, use_graphs=False)
+        ref.table_keys, ref.table_vals = py.table_keys, py.table_vals
+        want[q] = ref.noisy_labels(x, 24, 0.5, seed=5).clone().cpu()
+    assert not (torch.equal(want[long_q], want[short_q]) and torch.equal(want[long_q], want[other_q])), "questions must matter"
+    for q in (short_q, long_q, other_q, short_q):          # back and forth: graphs are keyed by the question length
+        nat.set_question(q)
+        py.set_question(q)
+        got = nat.noisy_labels(x, 24, 0.5, seed=5).cpu()
+        assert torch.equal(got, want[q]), q
+        assert torch.equal(py.noisy_labels(x, 24, 0.5, seed=5).clone().cpu(), want[q]), q
+    with pytest.raises(AssertionError):
+        nat.set_question(tuple(range(3, 3 + len(long_q) + 1)))        # longer than the engine was built for

@@ -240,3 +240,52 @@ def test_finetune_agent_loop_and_lr_schedule():
     agent.finalize()
     assert len(hist["train_loss"]) >= 2 and hist["train_loss"][-1] < hist["train_loss"][0]
     assert agent.best_state is not None and agent.best_val_loss == min(hist["val_loss"])
+
+
+def test_per_row_instructions_equal_one_question_at_a_time():
+    """MiniGPTBase.forward trains every sample on ITS instruction (minigpt_base.py:323-362): a batch whose rows carry
+    different suffix ids gives each row the token losses of a batch-of-one run under that question."""
+    cfg = ModelConfig.tiny()
+    sd, eng, tr = _trainer(cfg, seed=51)
+    S = cfg.vit.img_size
+    images = torch.rand(3, 3, S, S, generator=torch.Generator().manual_seed(2)).cuda()
+    answers = torch.tensor([[20, 2, -100], [21, 22, 2], [23, 24, 2]])
+    sfx = torch.tensor([[7, 8, 9], [30, 31, 32], [40, 41, 42]])
+    tr.forward(images, answers, 0.25, seed=4, step=9, suffix_ids=sfx)
+    tok = tr.last["tok"].clone()
+    for b in range(3):
+        eng.set_question(sfx[b].tolist())
+        tr.forward(images[b:b + 1], answers[b:b + 1], 0.25, seed=4, step=9, sample_offset=b)
+        assert torch.equal(tr.last["tok"][0], tok[b]), b
+    assert not torch.equal(tok[0], tok[1])
+    with pytest.raises(AssertionError):
+        tr.forward(images, answers, 0.0, suffix_ids=torch.zeros(3, 9, dtype=torch.long))      # longer than the engine's
+
+
+def test_finetune_agent_buckets_by_instruction_length_and_shards_by_rank():
+    from certifiedgpt_b200.agents.minigpt4_finetune_agent import MiniGPT4FineTuneAgent, collate, linear_warmup_cosine_lr
+    cfg = ModelConfig.tiny()
+    sd, eng, _ = _trainer(cfg, seed=47)
+    S = cfg.vit.img_size
+    g = torch.Generator().manual_seed(3)
+    lens = [3, 5, 3, 5, 5, 3, 3, 5, 4, 4]
+    train = [{"image": torch.rand(3, S, S, generator=g), "answer_ids": [20 + i % 3, 2],
+              "suffix_ids": list(range(7, 7 + lens[i]))} for i in range(10)]
+    agent = MiniGPT4FineTuneAgent(eng, train, None, batch_size=2, max_epoch=2, init_lr=3e-3, min_lr=1e-3, warmup_steps=2,
+                                  warmup_start_lr=1e-3, warmup_max_lr=3e-3, weight_decay=0.0, max_answer=4)
+    b0 = agent._batch_indices(train, 0, shuffle=True)
+    assert len(b0) == 5 and sorted(j for b in b0 for j in b) == list(range(10))
+    assert all(len({lens[j] for j in b}) == 1 for b in b0)                       # one instruction length per batch
+    assert b0 != agent._batch_indices(train, 1, shuffle=True)                    # reshuffled every epoch
+    agent.rank, agent.world = 1, 2                                               # DistributedSampler-style sharding
+    assert agent._batch_indices(train, 0, shuffle=True) == b0[:4][1::2]
+    agent.rank, agent.world = 0, 1
+    images, answers, sfx = collate([train[j] for j in b0[0]])
+    assert sfx.shape == (2, lens[b0[0][0]]) and answers.shape == (2, 2)
+    # the first step runs at AdamW's init_lr, step k at the rate the scheduler set after step k - 1 (:176-178)
+    seen = []
+    orig = agent.trainer.train_step
+    agent.trainer.train_step = lambda *a, **kw: (seen.append(kw["lr"]), orig(*a, **kw))[1]
+    agent.train(0)
+    want = [3e-3] + [linear_warmup_cosine_lr(0, s, **agent.sched) for s in range(4)]
+    assert seen == pytest.approx(want)
