@@ -422,10 +422,9 @@ def norm_rows(x, gamma, beta, eps, out, *, rms=False, rows=None, gather=None):
 
 
 def attn_vit_supported(*, B, H, T, head_dim):
-    """True when the pipelined head-major tcgen05 attention kernel (csrc/attn_vit.cu) serves this non-causal shape."""
-    E = 1 if T > 256 else 0
-    return (64 < head_dim <= (96 if E else 128) and head_dim % 8 == 0 and 1 <= T - E <= 256
-            and B * H * T < 2 ** 31)
+    """True when a head-major tcgen05 attention kernel serves this non-causal shape: csrc/attn_vit.cu up to 256 (+1 cls)
+    keys, csrc/attn_long.cu (multi-tile, exact two-pass softmax) beyond."""
+    return 64 < head_dim <= 128 and head_dim % 8 == 0 and T >= 1 and B * H * T < 2 ** 31
 
 
 def attention(q, k, v, o, *, B, H, Tq, Tk, head_dim, scale, q_rows_per_batch=None,

@@ -387,7 +387,8 @@ int attention(const cgpt_attn_args* a, cudaStream_t stream) {
   CGPT_REQUIRE(a->B > 0 && a->B <= 65535 && a->H > 0 && a->Tq > 0 && a->Tk > 0,
                "attention: bad sizes B=%d H=%d Tq=%d Tk=%d", a->B, a->H, a->Tq, a->Tk);
   CGPT_REQUIRE(a->head_dim % 8 == 0 && a->head_dim <= 128, "attention: head_dim %d unsupported", a->head_dim);
-  if (a->head_major) return attention_vit(a, stream);   // head-major q / k / v: the pipelined tcgen05 kernel or an error
+  if (a->head_major)   // head-major q / k / v: the pipelined tcgen05 kernels (<= 256 (+1) keys: one-tile, else multi-tile) or an error
+    return attn_vit_supported(a) ? attention_vit(a, stream) : attention_long(a, stream);
   CGPT_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 2 == 0,
                "attention: leading dims must keep 16-byte row alignment");
   CGPT_REQUIRE(a->P >= 0 && a->P <= a->Tk && (a->P == 0 || (a->kp && a->vp)), "attention: bad prefix");

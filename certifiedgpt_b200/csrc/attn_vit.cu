@@ -345,56 +345,61 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
       // Scores against the cls key (this row, returned) and of the cls query against main key q_main (thread <-> key,
       // into xs), read from the TMA-loaded, swizzled Q / K tiles in shared memory.  All the 16-byte loads of a row are
       // issued before the first multiply (hd <= 96: at most 12 chunks).
-      auto cls_scores = [&](int it) -> float {
-        const uint32_t ph = it & 1;
-        float* xb = xbase + (it & 1) * XBUF;
-        const float* xk = xb; const float* xq = xb + 256; float* xs = xb + 384;
+      // Part 1 (this row against the cls key, returned) runs while P_t.V of the previous item is in flight, part 2 (the
+      // cls query against main key q_main, into xs) while S_t of the item itself is; together they are the item's share
+      // of CUDA-core dot products, placed where the softmax thread would otherwise only wait.
+      uint4 tile[12];
+      auto dot = [&](const float* x, int nch) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+          if (c < nch) {
+            const float4 x0 = *reinterpret_cast<const float4*>(x + c * 8), x1 = *reinterpret_cast<const float4*>(x + c * 8 + 4);
+            acc += bf16_lo(tile[c].x) * x0.x + bf16_hi(tile[c].x) * x0.y + bf16_lo(tile[c].y) * x0.z + bf16_hi(tile[c].y) * x0.w +
+                   bf16_lo(tile[c].z) * x1.x + bf16_hi(tile[c].z) * x1.y + bf16_lo(tile[c].w) * x1.z + bf16_hi(tile[c].w) * x1.w;
+          }
+        }
+        return acc;
+      };
+      auto cls_key_score = [&](int it) -> float {
+        const float* xk = xbase + (it & 1) * XBUF;
         mbar_wait(&bar_xr[it & 1], (it >> 1) & 1);
-        mbar_wait(&bar_q[t], ph);
-        mbar_wait(bar_k, ph);
+        mbar_wait(&bar_q[t], it & 1);
         const int nch = hd >> 3;
         const uint8_t* qrow = sQ + t * 2 * VSUB + r * 128;
-        const uint8_t* krow = sK + q_main * 128;          // key index == q_main (requires q_main < nk_pad)
-        const bool kok = q_main < Tk_main;
-        uint4 tile[12];
-        auto dot = [&](const float* x) {
-          float acc = 0.f;
-#pragma unroll
-          for (int c = 0; c < 12; ++c) {
-            if (c < nch) {
-              const float4 x0 = *reinterpret_cast<const float4*>(x + c * 8), x1 = *reinterpret_cast<const float4*>(x + c * 8 + 4);
-              acc += bf16_lo(tile[c].x) * x0.x + bf16_hi(tile[c].x) * x0.y + bf16_lo(tile[c].y) * x0.z + bf16_hi(tile[c].y) * x0.w +
-                     bf16_lo(tile[c].z) * x1.x + bf16_hi(tile[c].z) * x1.y + bf16_lo(tile[c].w) * x1.z + bf16_hi(tile[c].w) * x1.w;
-            }
-          }
-          return acc;
-        };
 #pragma unroll
         for (int c = 0; c < 12; ++c)
           if (c < nch) tile[c] = *reinterpret_cast<const uint4*>(qrow + (c >> 3) * VSUB + (((c & 7) ^ (r & 7)) << 4));
-        const float a1 = dot(xk);
-        if (kok) {
+        const float a1 = dot(xk, nch);
+        return row_ok ? a1 : -INFINITY;
+      };
+      auto cls_query_score = [&](int it) {
+        float* xb = xbase + (it & 1) * XBUF;
+        mbar_wait(bar_k, it & 1);
+        if (q_main < Tk_main) {
+          const int nch = hd >> 3;
+          const uint8_t* krow = sK + q_main * 128;        // key index == q_main (requires q_main < nk_pad)
 #pragma unroll
           for (int c = 0; c < 12; ++c)
             if (c < nch) tile[c] = *reinterpret_cast<const uint4*>(krow + (c >> 3) * kv_sub + (((c & 7) ^ (q_main & 7)) << 4));
-          xs[1 + q_main] = dot(xq);
+          xb[384 + 1 + q_main] = dot(xb + 256, nch);
         }
         mbar_arrive(bar_x);
-        return row_ok ? a1 : -INFINITY;
       };
       float s_x = -INFINITY;
-      if (n_mine > 0) {
-        if (E) s_x = cls_scores(0);
-        mbar_arrive(bar_qkr);              // this thread no longer reads the Q / K tiles of item 0
-      }
+      if (n_mine > 0 && E) s_x = cls_key_score(0);
       int it = 0;
       for (int item = first_item; item < p.n_items; item += grid, ++it) {
         const uint32_t ph = it & 1;
         const int h = item % p.H, b = item / p.H;
         const float* xv = xbase + (it & 1) * XBUF + 128;
-        if (threadIdx.x == 128) VA_STAMP(5);
+        const bool stamp = threadIdx.x == 128 && it == (n_mine > 2 ? 1 : 0);   // a steady-state item
+        if (stamp) VA_STAMP(5);
+        if (E) cls_query_score(it);          // while S_t of this item is being formed
+        mbar_arrive(bar_qkr);                // this thread no longer reads the Q / K tiles of this item
+        if (stamp) VA_STAMP(6);
         mbar_wait(&bar_s[t], ph);
-        if (threadIdx.x == 128) VA_STAMP(7);
+        if (stamp) VA_STAMP(7);
         tcgen05_fence_after();
         // pass 1: row max of the raw scores (mask: padded keys).  16-column TMEM loads, the next one in flight
         // while the current is reduced; full chunks skip the mask.
@@ -427,7 +432,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
           }
         }
         if (mx == -INFINITY) mx = 0.f;
-        if (threadIdx.x == 128) VA_STAMP(8);
+        if (stamp) VA_STAMP(8);
         const float neg_ms = -mx * p.scale_log2e;
         // pass 2: P = exp2(s * scale - max * scale) as packed bf16, IN PLACE over the S region: the 16 keys of
         // chunk c go to columns [c / 2, c / 2 + 8), always behind the columns still to be read
@@ -472,16 +477,13 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
         tmem_st_wait();             // this thread's P stores have landed in TMEM
         tcgen05_fence_before();     // ... and are ordered before the P.V product the MMA thread issues after the barrier
         mbar_arrive(&bar_p[t]);
-        if (threadIdx.x == 128) VA_STAMP(9);
-        // while P_t.V runs: the cls scores of the NEXT item (its Q tile and K landed long ago)
-        if (item + grid < p.n_items) {
-          if (E) s_x = cls_scores(it + 1);
-          mbar_arrive(bar_qkr);              // this thread no longer reads the Q / K tiles of item it + 1
-        }
-        if (threadIdx.x == 128) VA_STAMP(12);
+        if (stamp) VA_STAMP(9);
+        // while P_t.V runs: the score of the NEXT item's cls key (its Q tile landed long ago)
+        if (E && item + grid < p.n_items) s_x = cls_key_score(it + 1);
+        if (stamp) VA_STAMP(12);
         // ---- epilogue: O_t / rowsum (+ the cls key's rank-1 term) -> bf16 -> shared-memory transpose -> global
         mbar_wait(&bar_o[t], ph);
-        if (threadIdx.x == 128) VA_STAMP(10);
+        if (stamp) VA_STAMP(10);
         tcgen05_fence_after();
         const float inv = sum > 0.f ? 1.f / sum : 0.f;
         const uint32_t o_addr = t_lane + 128;
@@ -495,13 +497,15 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
           tmem_ld_wait();
           uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float f0 = __uint_as_float(v[i]), f1 = __uint_as_float(v[i + 1]);
+          for (int i = 0; i < 32; i += 4) {
+            float f0 = __uint_as_float(v[i]), f1 = __uint_as_float(v[i + 1]), f2 = __uint_as_float(v[i + 2]),
+                  f3 = __uint_as_float(v[i + 3]);
             if (E) {
-              f0 += p_x * xv[(c + i) & 127];
-              f1 += p_x * xv[(c + i + 1) & 127];
+              const float4 x4 = *reinterpret_cast<const float4*>(xv + ((c + i) & 127));   // one broadcast 16-byte load
+              f0 += p_x * x4.x; f1 += p_x * x4.y; f2 += p_x * x4.z; f3 += p_x * x4.w;
             }
             w[i >> 1] = pack_bf16x2(f0 * inv, f1 * inv);
+            w[(i >> 1) + 1] = pack_bf16x2(f2 * inv, f3 * inv);
           }
           uint4* mine = reinterpret_cast<uint4*>(patch + lane * OPITCH);
           mine[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -523,7 +527,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
         }
         tcgen05_fence_before();     // this thread's TMEM reads of O_t are done before the next S_t may overwrite the region
         mbar_arrive(&bar_free[t]);
-        if (threadIdx.x == 128) VA_STAMP(11);
+        if (stamp) VA_STAMP(11);
       }
     }
   }

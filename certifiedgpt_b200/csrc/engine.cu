@@ -416,7 +416,8 @@ int vit_forward(Engine* E, const void* patches, int B, void* out, cudaStream_t s
   CGPT_TRY(set_rows_f32(res, static_cast<long long>(T) * D, E->cls_pos, D, B, s));
   const float scale = 1.0f / sqrtf(static_cast<float>(E->vhd));
   // head-major q / k / v ([3][B][H][T][hd], written by the QKV GEMM's scatter epilogue) + the pipelined tcgen05
-  // attention kernel whenever the shape allows (224 px: T = 257); row-major + the generic dispatcher otherwise (448 px)
+  // attention kernels whenever the shape allows (224 px: T = 257, one key tile + cls; 448 px: T = 1025, multi-tile);
+  // row-major + the generic dispatcher otherwise (head dims <= 64: the small test models)
   cgpt_attn_args hm;
   memset(&hm, 0, sizeof(hm));
   const long long MD = static_cast<long long>(M) * D;
@@ -424,7 +425,7 @@ int vit_forward(Engine* E, const void* patches, int B, void* out, cudaStream_t s
   hm.q_rows_per_batch = T; hm.kv_rows_per_batch = T; hm.o = b.v_att; hm.ldo = D;
   hm.B = B; hm.H = c.vit_heads; hm.Tq = T; hm.Tk = T; hm.head_dim = E->vhd; hm.scale = scale; hm.head_major = 1;
   static const bool no_hm = getenv("CGPT_VIT_ROW_MAJOR") != nullptr;   // A/B switch: the round-1 layout and kernel
-  const bool use_hm = !no_hm && attn_vit_supported(&hm);
+  const bool use_hm = !no_hm && (attn_vit_supported(&hm) || attn_long_supported(&hm));
   for (int i = 0; i < c.vit_depth; ++i) {
     const VitLayer& L = E->vit[i];
     CGPT_TRY(norm_rows(res, D, CGPT_DT_F32, L.ln1w, L.ln1b, c.vit_eps, M, D, b.v_xn, D, CGPT_DT_BF16, 0, 0, 0, 0, s));

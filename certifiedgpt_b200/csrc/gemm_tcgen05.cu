@@ -48,7 +48,7 @@ struct GemmCfg {
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int RED_STAGE_BYTES = 8 * 32 * 20 * 4;   // 8 epilogue warps x [32 rows][16 + 4 pad] fp32
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/ +
-                                    RED_STAGE_BYTES;
+                                    RED_STAGE_BYTES + 2 * 32 * 8 /*head-major column offsets*/;
   static_assert(B_SUB % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
   static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
 };
@@ -136,7 +136,8 @@ __device__ __forceinline__ void load_resid16(const EpiParams& p, long long out_r
 // instantiation so that the hot epilogue loop of every other GEMM keeps its code size)
 template <bool HM>
 __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiParams& p, const float* bias_s,
-                                                 const float* resid_r, int m, long long out_row, int n0) {
+                                                 const float* resid_r, int m, long long out_row, int n0,
+                                                 const long long* hm_off = nullptr) {
   constexpr int NC = 16;
   float v[NC];
 #pragma unroll
@@ -192,16 +193,10 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
     for (int i = 0; i < NC; ++i) v[i] += resid_r[i];
   }
   if constexpr (HM) {
-    // 8-element pieces never straddle a head (hd % 8 == 0); which / h / d are the same for the whole warp
+    // hm_off[i]: offset of the i-th 8-column piece of this chunk (shared-memory table, one entry per piece and tile)
 #pragma unroll
     for (int i = 0; i < NC; i += 8) {
-      const int n = n0 + i;
-      const int which = (n >= p.hm_D) + (n >= 2 * p.hm_D);
-      const int rem = n - which * p.hm_D;
-      const int h = static_cast<int>((static_cast<float>(rem) + 0.5f) * p.hm_inv_hd);
-      const int d = rem - h * p.hm_hd;
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + which * p.hm_ws + out_row +
-                         static_cast<long long>(h) * p.hm_T * p.hm_hd + d;
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row + hm_off[i >> 3];
       __stcs(reinterpret_cast<uint4*>(o),
              make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
                         pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7])));
@@ -232,7 +227,7 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t* acc, const EpiP
 template <bool HM>
 __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams& epi, const float* bias_s,
                                                 int m, long long out_row, bool row_ok, int n_base, int N,
-                                                int c0, int c1) {
+                                                int c0, int c1, const long long* hm_tbl = nullptr) {
   uint32_t r0[16], r1[16];
   float rr0[16], rr1[16];
   const bool has_res = epi.resid != nullptr && row_ok && !epi.red_inplace;
@@ -245,7 +240,8 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams&
       tmem_ld_x16(t_row + (c + 1) * 16, r1);
       if (has_res && n_base + (c + 1) * 16 < N) load_resid16(epi, out_row, n_base + (c + 1) * 16, rr1);
     }
-    if (row_ok && n_base + c * 16 < N) epilogue_store16<HM>(r0, epi, bias_s + c * 16, rr0, m, out_row, n_base + c * 16);
+    if (row_ok && n_base + c * 16 < N)
+      epilogue_store16<HM>(r0, epi, bias_s + c * 16, rr0, m, out_row, n_base + c * 16, HM ? hm_tbl + 2 * c : nullptr);
     if (c + 1 < c1) {
       tmem_ld_wait();
       if (c + 2 < c1) {
@@ -253,7 +249,8 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_row, const EpiParams&
         if (has_res && n_base + (c + 2) * 16 < N) load_resid16(epi, out_row, n_base + (c + 2) * 16, rr0);
       }
       if (row_ok && n_base + (c + 1) * 16 < N)
-        epilogue_store16<HM>(r1, epi, bias_s + (c + 1) * 16, rr1, m, out_row, n_base + (c + 1) * 16);
+        epilogue_store16<HM>(r1, epi, bias_s + (c + 1) * 16, rr1, m, out_row, n_base + (c + 1) * 16,
+                             HM ? hm_tbl + 2 * (c + 1) : nullptr);
     }
   }
 }
@@ -434,6 +431,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* bias_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // [2][256]
   float* red_stage = bias_smem + 2 * 256;                                                // [8 warps][32][20]
+  long long* hm_tbl = reinterpret_cast<long long*>(red_stage + 8 * 32 * 20);             // [2 acc stages][32 pieces of 8 columns]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -569,6 +567,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         const int n = n_base + epi_tid;
         bias_s[epi_tid] = n < N ? __ldg(epi.bias + n) : 0.f;
       }
+      if constexpr (MODE == MODE_HM) {
+        // element offset of every 8-column piece of this tile inside the head-major output, minus the row part:
+        // worked out once per tile by 32 threads instead of once per piece and thread (8-element pieces never straddle a
+        // head: hd % 8 == 0)
+        if (epi_tid < BN / 8) {
+          const int n = n_base + epi_tid * 8;
+          const int which = (n >= epi.hm_D) + (n >= 2 * epi.hm_D);
+          const int rem = n - which * epi.hm_D;
+          const int h = static_cast<int>((static_cast<float>(rem) + 0.5f) * epi.hm_inv_hd);
+          hm_tbl[acc * 32 + epi_tid] = which * epi.hm_ws + static_cast<long long>(h) * epi.hm_T * epi.hm_hd + (rem - h * epi.hm_hd);
+        }
+      }
       {
         // pull this thread's residual row segment towards L2 while the tile's MMAs still run: the
         // row-per-thread residual loads below are latency-bound (25k cycles per tile vs 11k of MMA otherwise)
@@ -614,7 +624,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                                    half == 0 ? 0 : NCH0, half == 0 ? NCH0 : NCH);
       } else {
         epilogue_chunks<MODE == MODE_HM>(t_row, epi, bias_s, m, out_row, row_ok, n_base, N, half == 0 ? 0 : NCH0,
-                                         half == 0 ? NCH0 : NCH);
+                                         half == 0 ? NCH0 : NCH, hm_tbl + acc * 32);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -778,8 +788,10 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   // it.  CGPT_GEMM_RED_DIRECT=1 / CGPT_GEMM_RED_COALESCED=1 force one form for experiments.
   if (p.red_inplace && p.ldo % 4 == 0 && !getenv("CGPT_GEMM_RED_DIRECT") &&
       (K <= 2048 || getenv("CGPT_GEMM_RED_COALESCED")))
-    p.red_inplace = getenv("CGPT_GEMM_RED_NO_RMW") ? 2 : 3;   // 3 = coalesced load + add + store (A/B switch keeps the RED form)
-  if (p.red_inplace && p.ldo % 4 == 0 && getenv("CGPT_GEMM_RMW_ALL")) p.red_inplace = 3;   // experiment: RMW for the long-K GEMMs too
+    p.red_inplace = getenv("CGPT_GEMM_RED_RMW") ? 3 : 2;   // 3 = coalesced load + add + store instead of RED: measured SLOWER
+                                                           // on the ViT proj GEMM (834 vs 952 TFLOP/s at batch 1024, one box,
+                                                           // gpurun_out/r2_c4_prof_*.log): the loads sit on the tile's critical
+                                                           // path, the reductions are fire-and-forget; kept as an experiment
   p.dbg = reinterpret_cast<long long*>(getenv("CGPT_GEMM_DBG") ? strtoull(getenv("CGPT_GEMM_DBG"), nullptr, 0) : 0ull);
   p.hm_T = 0; p.hm_H = 0; p.hm_hd = 0; p.hm_D = 0; p.hm_inv_hd = 0.f; p.hm_ws = 0;
   if (e->hm_T > 0) {

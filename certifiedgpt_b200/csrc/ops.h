@@ -53,6 +53,8 @@ int attn_umma_supported(const cgpt_attn_args* a);
 int attention_umma(const cgpt_attn_args* a, cudaStream_t stream);
 int attn_vit_supported(const cgpt_attn_args* a);
 int attention_vit(const cgpt_attn_args* a, cudaStream_t stream);
+int attn_long_supported(const cgpt_attn_args* a);
+int attention_long(const cgpt_attn_args* a, cudaStream_t stream);
 int attn_prefill_supported(const cgpt_attn_args* a);
 int attention_prefill(const cgpt_attn_args* a, cudaStream_t stream);
 int rope_split(void* qkv, long long ld, int rows, int T, int H, int head_dim, int pos0, const float* cos_t,

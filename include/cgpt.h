@@ -196,7 +196,8 @@ typedef struct cgpt_attn_args {
                         mma.sync flash kernel), 1 = single-token KV-cache kernel (Tq == 1), 2 = force flash */
   int head_major;    /* 1: q, k, v are HEAD-MAJOR [B][H][T][head_dim] blocks (what the fused-QKV GEMM writes with
                         cgpt_gemm_epilogue.hm_T; ldq / ldk / ldv unused, Tq == Tk == rows per batch): served by the
-                        pipelined tcgen05 kernel (csrc/attn_vit.cu), non-causal, <= 256 (+1 cls) keys, 64 < hd <= 128 */
+                        pipelined tcgen05 kernels, non-causal, 64 < hd <= 128: csrc/attn_vit.cu up to 256 (+1 cls) keys
+                        (224 px ViT), csrc/attn_long.cu beyond (448 px ViT, T = 1025: key tiles, two-pass softmax) */
 } cgpt_attn_args;
 int cgpt_attention(const cgpt_attn_args* args, void* stream);
 

@@ -168,6 +168,25 @@ def test_head_major_rejects_unsupported_shapes(lib):
     q = torch.zeros(2 * 4 * 300 * 88, device="cuda", dtype=torch.bfloat16)
     out = torch.empty(2 * 300, 4 * 88, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(lib.CgptError):
-        lib.attention(q, q, q, out, B=2, H=4, Tq=300, Tk=300, head_dim=88, scale=1.0, head_major=True)
+        lib.attention(q[:2 * 4 * 300 * 64], q, q, out, B=2, H=4, Tq=300, Tk=300, head_dim=64, scale=1.0, head_major=True)
     with pytest.raises(lib.CgptError):
         lib.attention(q, q, q, out, B=2, H=4, Tq=100, Tk=100, head_dim=88, scale=1.0, head_major=True, causal=True)
+
+
+# ------------------------------------------------------------------ multi-tile kernel (attn_long.cu): 448 px ViT, T = 1025
+@pytest.mark.parametrize("B,H,T,hd", [
+    (2, 16, 1025, 88),      # EVA ViT-g at 448 px: 9 query tiles x 9 key tiles, the last ones hold one row
+    (1, 2, 1025, 88),
+    (3, 4, 300, 88),        # 3 tiles, ragged last tile (44 rows)
+    (2, 3, 258, 96),        # just past the one-tile kernel's range
+    (2, 2, 640, 128),       # 5 full tiles, hd = 128
+    (5, 4, 513, 72),        # odd tile count, one-row last tile, hd = 72
+])
+def test_head_major_multi_tile_kernel(lib, B, H, T, hd):
+    _run_head_major(lib, B, H, T, hd, seed=T + hd)
+
+
+def test_multi_tile_kernel_many_units_and_determinism(lib):
+    a, _ = _run_head_major(lib, 12, 16, 1025, 88, seed=9)      # 1728 units: ~12 per persistent CTA
+    b, _ = _run_head_major(lib, 12, 16, 1025, 88, seed=9)
+    assert torch.equal(a, b)

@@ -118,6 +118,30 @@ def test_448px_path_matches_oracle():
     assert torch.equal(nat.noisy_labels(x, 3, 0.25, seed=4).cpu(), eng.noisy_labels(x, 3, 0.25, seed=4).cpu())
 
 
+def test_448px_full_width_vit_layers_match_oracle():
+    """448 px at the real ViT width (1408 = 16 heads x 88, T = 1025): the QKV GEMM's head-major scatter and the multi-tile
+    tcgen05 attention kernel (attn_long.cu) inside two full-width blocks, against the fp32 oracle (rel 2e-2)."""
+    from certifiedgpt_b200.config import QFormerConfig, VitConfig
+    from certifiedgpt_b200.engine import MiniGPT4Engine
+    cfg = ModelConfig(vit=VitConfig(img_size=448, depth=2), qf=QFormerConfig(layers=2),
+                      llm=LlmConfig(hidden=512, layers=1, heads=4, inter=1024, vocab=512))
+    assert cfg.vit.tokens == 1025 and cfg.vit.head_dim == 88
+    sd = round_to_bf16(random_state_dict(cfg, seed=19))
+    table = [((t,), t % 5) for t in range(3, cfg.llm.vocab)]
+    eng = MiniGPT4Engine(cfg, sd, (1, 4), (6, 7, 8), table, 6, max_new_tokens=1)
+    images = torch.randn(2, 3, 448, 448, generator=torch.Generator().manual_seed(5))
+    got, ref = {}, {}
+    eng.forward_images(images.cuda(), collect=got)
+    with torch.no_grad():
+        mo.encode_img(sd, cfg, images, collect=ref)
+    for k in ("embed", "block0", "block1", "image_embeds", "layer1"):
+        assert _rel(got[k], ref[k]) < 2e-2, k
+    from certifiedgpt_b200.native import NativeMiniGPT4Engine
+    nat = NativeMiniGPT4Engine.from_engine(eng)
+    x = torch.rand(3, 448, 448, generator=torch.Generator().manual_seed(6)).cuda()
+    assert torch.equal(nat.noisy_labels(x, 3, 0.25, seed=4).cpu(), eng.noisy_labels(x, 3, 0.25, seed=4).clone().cpu())
+
+
 def test_full_width_llm_matches_oracle():
     """Llama-2-7B widths (4096 / 32 heads x 128 / 11008 / vocab 32000), 2 layers: logits within bf16
     tolerance and greedy ids exact where the oracle margin is safe."""
@@ -162,9 +186,9 @@ def test_bench_shape_32_layer_llama_matches_oracle_per_sample():
     """BASELINE configs[1]'s OWN shape - ViT-g 39L, Q-Former 12L, Llama-2-7B 32L (7 B distinct random weights), prompt
     7 + 32 + 40, max_new_tokens 4 - against the fp32 CPU oracle on identical injected noise: image embeddings within
     rel 2e-2, first-step logits within rel 6e-2; generated ids and labels equal per sample wherever the oracle's top-2 margin is safe
-    at every step.  "Safe" = above north_star's 1e-2 AND above the bf16 error the logits actually carry after 39 + 12 + 32
-    layers (4 x the measured max |logit error| of the first step): a margin below the arithmetic's own error cannot pin
-    an argmax, for this engine or for the reference's fp16 autocast.  The weights are drawn on the GPU, rounded to bf16
+    at every step.  "Safe" = above north_star's 1e-2 AND above twice the error the bf16 logits of that sample actually
+    carry after 39 + 12 + 32 layers (measured on the first step): a margin below the arithmetic's own error cannot pin an
+    argmax, for this engine or for the reference's fp16 autocast.  The weights are drawn on the GPU, rounded to bf16
     and copied to the host for the oracle (31 GB fp32 there)."""
     import bench
     from certifiedgpt_b200.engine import MiniGPT4Engine
@@ -197,16 +221,26 @@ def test_bench_shape_32_layer_llama_matches_oracle_per_sample():
     # at the depths of the other tests, not across the full 83-layer stack; the bound here is 6e-2
     rel_logits = _rel(got["first_logits"], orc.last["first_logits"])
     assert rel_logits < 6e-2, rel_logits
-    err = (got["first_logits"].float().cpu() - orc.last["first_logits"]).abs().max().item()
-    floor = max(1e-2, 4.0 * err)
-    safe = (margins > floor).all(dim=1)
-    print(f"full shape: logits rel {rel_logits:.4f}, max |logit error| {err:.4f}, margin floor {floor:.4f}, safe draws {int(safe.sum())}/{B}, "
-          f"margins min/median {margins.min().item():.4f}/{margins.median().item():.4f}")
-    assert int(safe.sum()) >= 3, margins
+    # Per sample: eb = max over the vocabulary of |logit error| at the first step.  If the oracle's top-2 margin exceeds
+    # 2 * eb, no rounding the engine made can change the argmax - a provable statement for step 0, and with teacher-equal
+    # prefixes the later steps see the same kind of error, so the same bound is applied to them.
+    diff = (got["first_logits"].float().cpu() - orc.last["first_logits"]).abs()
+    eb = diff.max(dim=1).values
+    floor = torch.clamp(2.0 * eb, min=1e-2)
     gids = got["ids"].cpu().long()
-    assert torch.equal(gids[safe], ref_ids[safe]), (gids, ref_ids, margins)
-    assert torch.equal(lab[safe], ref_lab[safe])
-    # the first token is pinned by the first-step margin alone
-    safe1 = margins[:, 0] > floor
-    assert torch.equal(gids[safe1, 0], ref_ids[safe1, 0])
+    safe0 = margins[:, 0] > floor
+    safe = (margins > floor[:, None]).all(dim=1)
+    agree = (gids == ref_ids).float().mean().item()
+    print(f"full shape: logits rel {rel_logits:.4f}, per-sample max |logit error| {eb.min().item():.3f}..{eb.max().item():.3f}, "
+          f"first-token-safe draws {int(safe0.sum())}/{B}, all-steps-safe draws {int(safe.sum())}/{B}, "
+          f"margins min/median {margins.min().item():.4f}/{margins.median().item():.4f}, tokens equal {agree:.2f}")
+    assert torch.equal(gids[safe0, 0], ref_ids[safe0, 0])         # first token: exact wherever the margin pins it
+    # the contrapositive on the oracle's own logits: where the first token differs, the two candidates are closer than the
+    # error band in the fp32 oracle too
+    rl = orc.last["first_logits"]
+    for i in torch.nonzero(gids[:, 0] != ref_ids[:, 0]).flatten().tolist():
+        gap = (rl[i, ref_ids[i, 0]] - rl[i, gids[i, 0]]).item()
+        assert 0 <= gap <= 2.0 * eb[i].item(), (i, gap, eb[i].item())
+    assert torch.equal(gids[safe], ref_ids[safe]) and torch.equal(lab[safe], ref_lab[safe])
+    assert agree >= 0.5                                            # and most tokens agree even inside the error band
     assert gids.shape == (B, 4) and (gids[:, 0] != cfg.llm.eos_id).all()
