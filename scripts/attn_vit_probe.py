@@ -57,10 +57,9 @@ run_hm()
 torch.cuda.synchronize()
 del os.environ["CGPT_ATTN_DBG"]
 d = dbg.view(sms, 16).cpu()
-names = {5: "item start", 6: "cls query scores", 7: "S ready", 8: "row max done", 9: "P written", 12: "next cls key score",
-         10: "O ready", 11: "O stored"}
+names = {5: "item start", 7: "S ready", 8: "row max done", 9: "P written", 12: "next cls scores", 10: "O ready", 11: "O stored"}
 base = d[:, 5]
-for k in (6, 7, 8, 9, 12, 10, 11):
+for k in (7, 8, 9, 12, 10, 11):
     v = (d[:, k] - base).float()
     print(f"  softmax thread 128: {names[k]:18s} +{v.median().item():8.0f} cycles (median over CTAs)")
 print(f"  MMA thread: first S issued -> done = {(d[:, 3] - d[:, 2]).float().median().item():.0f} cycles for "

@@ -42,6 +42,18 @@ def main():
     res1 = single.certify(x, n0, n, 0.001, 64)
     ok = (res == res1 and torch.equal(sel, single.last_counts_selection)
           and torch.equal(est, single.last_counts_estimation) and int(est.sum()) == n)
+    # several images per pass (cgpt_certify_batch): draws of EVERY image sharded over the ranks, one all-reduce of all the
+    # count-vector pairs; per image the same counts / label / radius as single-GPU, one-image-at-a-time certification
+    if Engine is NativeMiniGPT4Engine:
+        xs = [torch.rand(3, S, S, generator=torch.Generator().manual_seed(2000 + i)).to(dev) for i in range(3)]
+        many = Smooth(eng, 10, 0.25, seed=43, process_group=True)
+        got = many.certify_batch(xs, n0, n, 0.001, 96)
+        one = Smooth(eng, 10, 0.25, seed=43)
+        for k, xk in enumerate(xs):
+            want = one.certify(xk, n0, n, 0.001, 64)
+            d = many.last_batch_detail[k]
+            ok = ok and got[k] == want and torch.equal(d["counts_selection"], one.last_counts_selection) \
+                and torch.equal(d["counts_estimation"], one.last_counts_estimation)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     # data-parallel fine-tune step: every rank trains on its own images, the llama_proj gradient is averaged over the
