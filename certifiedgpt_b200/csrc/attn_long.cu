@@ -2,13 +2,15 @@
 //   EVA ViT self-attention at 448 px, T = 1025 tokens, 16 heads x 88 - the resolution of every shipped reference config
 //   (configs/eval_configs/vqav2_eval_noise_0.yaml:35; eva_vit.py:123-153).
 // Head-major q, k, v ([B][H][T][hd], see attn_vit.cu).  Work unit = (sample, head, 128-query tile); keys in tiles of 128.
-// TMEM holds two S buffers of 128 x 128 fp32 and the O accumulator (128 x hd) - all of S (1025 columns) would not fit -
-// so softmax is EXACT two-pass: pass 1 forms S = Q K^T tile by tile only for the row maximum, pass 2 forms it again,
+// TMEM holds THREE S buffers of 128 x 128 fp32 (tile number modulo 3) and the O accumulator (128 x hd) - all of S (1025
+// columns) would not fit - so softmax is EXACT two-pass: pass 1 forms S = Q K^T tile by tile only for the row maximum, pass 2 forms it again,
 // turns it into P = exp2(s - max) in place (packed bf16, read back by the tensor core as the A operand of P.V) and
 // accumulates O += P V in TMEM across the key tiles: no online rescale of O, and the tensor pipe has the slack for the
 // second Q K^T (the kernel is MUFU-bound: 1025 exp2 per row).
 //   warp 0      TMA producer : Q tile, then the K / V tiles in consumption order through a 5-slot ring
-//   warp 1      MMA issuer   : S into buffer kt & 1, P.V of tile kt - 1 behind S of tile kt
+//   warp 1      MMA issuer   : S two tiles ahead of P.V (three S buffers), so a softmax group never waits for the tensor
+//                              core: with two buffers every S -> softmax -> P.V -> S hand-over (4 mbarrier round trips
+//                              per tile) sat on the critical path: 39k cycles per unit against 14k of MUFU + tensor work
 //   warps 4-7   softmax group 0: the EVEN key tiles;  warps 8-11  softmax group 1: the ODD key tiles (thread = query row);
 //               the two groups exchange row maximum and row sum through shared memory
 // The cls token is simply row 0 of the head block: tiles start at the block's first row, keys >= T are masked, rows >= T
@@ -65,13 +67,13 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
   uint64_t* empty = bars + LA_STAGES;               // [STAGES] MMA -> TMA
   uint64_t* bar_q = bars + 2 * LA_STAGES;           // Q tile landed
   uint64_t* bar_qfree = bar_q + 1;                  // the unit's last S product retired: Q slot free
-  uint64_t* bar_s = bar_q + 2;                      // [2] S in buffer b
-  uint64_t* bar_sr = bar_q + 4;                     // [2] pass 1: buffer b read by its softmax group (128 arrivals)
-  uint64_t* bar_p = bar_q + 6;                      // [2] pass 2: P in buffer b (128 arrivals)
-  uint64_t* bar_pv = bar_q + 8;                     // [2] P.V out of buffer b retired
-  uint64_t* bar_o = bar_q + 10;                     // O of the unit complete
-  uint64_t* bar_ofree = bar_q + 11;                 // O drained by both groups (256 arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 12);
+  uint64_t* bar_s = bar_q + 2;                      // [3] S in buffer b
+  uint64_t* bar_sr = bar_q + 5;                     // [3] pass 1: buffer b read by its softmax group (128 arrivals)
+  uint64_t* bar_p = bar_q + 8;                      // [3] pass 2: P in buffer b (128 arrivals)
+  uint64_t* bar_pv = bar_q + 11;                    // [3] P.V out of buffer b retired
+  uint64_t* bar_o = bar_q + 14;                     // O of the unit complete
+  uint64_t* bar_ofree = bar_q + 15;                 // O drained by both groups (256 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 16);
   float* xch = reinterpret_cast<float*>(tail + 256);                 // [2 unit parities][2 groups][max | sum][128]
   uint8_t* ostage = reinterpret_cast<uint8_t*>(xch + 2 * 2 * 2 * 128);   // [8 softmax warps][32 rows][LA_OPITCH]
 
@@ -87,7 +89,7 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
     tma_prefetch_desc(&map_k1); tma_prefetch_desc(&map_v0); tma_prefetch_desc(&map_v1);
     for (int i = 0; i < LA_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(bar_q, 1); mbar_init(bar_qfree, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&bar_s[i], 1); mbar_init(&bar_sr[i], 128); mbar_init(&bar_p[i], 128); mbar_init(&bar_pv[i], 1);
     }
     mbar_init(bar_o, 1); mbar_init(bar_ofree, 256);
@@ -102,7 +104,7 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr uint32_t O_COL = 256;
+  constexpr uint32_t O_COL = 384;   // S buffers at columns 0, 128, 256
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -126,10 +128,11 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
         tma_load_2d(sQ, &map_q0, bar_q, 0, row0 + qt * 128);
         tma_load_2d(sQ + LA_SUB, &map_q1, bar_q, 64, row0 + qt * 128);
         for (int kt = 0; kt < n; ++kt) push(&map_k0, &map_k1, row0 + kt * 128);          // pass 1
-        for (int kt = 0; kt < n; ++kt) {                                                  // pass 2: K_kt, then V_{kt-1}
+        for (int kt = 0; kt < n; ++kt) {                                                  // pass 2: K_kt, then V_{kt-2}
           push(&map_k0, &map_k1, row0 + kt * 128);
-          if (kt >= 1) push(&map_v0, &map_v1, row0 + (kt - 1) * 128);
+          if (kt >= 2) push(&map_v0, &map_v1, row0 + (kt - 2) * 128);
         }
+        if (n >= 2) push(&map_v0, &map_v1, row0 + (n - 2) * 128);
         push(&map_v0, &map_v1, row0 + (n - 1) * 128);
       }
     }
@@ -140,8 +143,8 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       const uint32_t idesc_o = make_idesc_bf16(128, p.pv_n) | (1u << 16);   // B (= V) is MN-major
       int stage = 0;
       uint32_t phase = 0;
-      int n_s1[2] = {0, 0}, n_pv[2] = {0, 0};   // pass-1 uses / P.V uses of each S buffer so far
-      int last_kind[2] = {0, 0};                // 0 = never used, 1 = pass-1 tile, 2 = pass-2 tile
+      int n_s1[3] = {0, 0, 0}, n_pv[3] = {0, 0, 0};   // pass-1 uses / P.V uses of each S buffer so far
+      int last_kind[3] = {0, 0, 0};                  // 0 = never used, 1 = pass-1 tile, 2 = pass-2 tile
       auto wait_free = [&](int b) {
         if (last_kind[b] == 1) mbar_wait(&bar_sr[b], (n_s1[b] - 1) & 1);
         else if (last_kind[b] == 2) mbar_wait(&bar_pv[b], (n_pv[b] - 1) & 1);
@@ -160,9 +163,11 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
         if (++stage == LA_STAGES) { stage = 0; phase ^= 1; }
       };
       int ui = 0;
+      long long seq = 0;                             // S tiles issued so far (both passes, all units): buffer = seq % 3
       for (int u = first_unit; u < p.n_units; u += grid, ++ui) {
+        const long long seq2 = seq + n;              // sequence number of this unit's first pass-2 tile
         auto issue_pv = [&](int j) {
-          const int b = j & 1;
+          const int b = static_cast<int>((seq2 + j) % 3);
           mbar_wait(&bar_p[b], (n_pv[b]) & 1);
           mbar_wait(&full[stage], phase);
           if (j == 0 && ui > 0) mbar_wait(bar_ofree, (ui - 1) & 1);     // the previous unit's O has been drained
@@ -178,21 +183,22 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
           if (++stage == LA_STAGES) { stage = 0; phase ^= 1; }
         };
         mbar_wait(bar_q, ui & 1);
-        for (int kt = 0; kt < n; ++kt) {              // pass 1: S only (row maximum)
-          const int b = kt & 1;
+        for (int kt = 0; kt < n; ++kt, ++seq) {       // pass 1: S only (row maximum)
+          const int b = static_cast<int>(seq % 3);
           wait_free(b);
           issue_s(b);
           ++n_s1[b];
           last_kind[b] = 1;
         }
-        for (int kt = 0; kt < n; ++kt) {              // pass 2: S again, P.V one tile behind
-          const int b = kt & 1;
+        for (int kt = 0; kt < n; ++kt, ++seq) {       // pass 2: S again, P.V two tiles behind
+          const int b = static_cast<int>(seq % 3);
           wait_free(b);
           issue_s(b);
           last_kind[b] = 2;
           if (kt == n - 1) umma_commit(bar_qfree);    // the unit's last read of the Q tile
-          if (kt >= 1) issue_pv(kt - 1);
+          if (kt >= 2) issue_pv(kt - 2);
         }
+        if (n >= 2) issue_pv(n - 2);
         issue_pv(n - 1);
         umma_commit(bar_o);
       }
@@ -201,10 +207,9 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
     // ------------------------------------------------------------------ softmax groups, thread = query row
     const int g = (warp - 4) >> 2;                    // group g owns the key tiles kt = g, g + 2, ...
     const int r = (warp & 3) * 32 + lane;
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * 128;
-    const uint32_t t_o = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + O_COL;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t t_o = t_lane + O_COL;
     uint8_t* patch = ostage + (warp - 4) * (32 * LA_OPITCH);
-    int cnt_s = 0;                                    // uses of bar_s[g] so far
     int ui = 0;
     for (int u = first_unit; u < p.n_units; u += grid, ++ui) {
       const int item = u / n, qt = u - item * n;
@@ -212,10 +217,14 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       float* xmax = xch + (ui & 1) * 512;             // [2 groups][128]
       float* xsum = xmax + 256;
       // ---- pass 1: row maximum over this group's key tiles
+      // S tile number of this unit's pass-1 tile 0 (2n tiles per unit): buffer = number % 3, its use number / 3
+      const long long seq1 = static_cast<long long>(ui) * 2 * n;
       float mx = -INFINITY;
       for (int kt = g; kt < n; kt += 2) {
-        mbar_wait(&bar_s[g], cnt_s & 1);
-        ++cnt_s;
+        const long long sq = seq1 + kt;
+        const int sb = static_cast<int>(sq % 3);
+        const uint32_t t_s = t_lane + sb * 128;
+        mbar_wait(&bar_s[sb], static_cast<uint32_t>((sq / 3) & 1));
         tcgen05_fence_after();
         const int kmax = T - kt * 128;                // keys [0, kmax) of this tile exist
         uint32_t va[16], vb[16];
@@ -242,7 +251,7 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
           }
         }
         tcgen05_fence_before();
-        mbar_arrive(&bar_sr[g]);
+        mbar_arrive(&bar_sr[sb]);
       }
       xmax[g * 128 + r] = mx;
       asm volatile("bar.sync 3, 256;" ::: "memory");
@@ -252,8 +261,10 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       // ---- pass 2: P = exp2(s * scale - max * scale), packed bf16 in place over the first 64 columns of the buffer
       float sum = 0.f;
       for (int kt = g; kt < n; kt += 2) {
-        mbar_wait(&bar_s[g], cnt_s & 1);
-        ++cnt_s;
+        const long long sq = seq1 + n + kt;
+        const int sb = static_cast<int>(sq % 3);
+        const uint32_t t_s = t_lane + sb * 128;
+        mbar_wait(&bar_s[sb], static_cast<uint32_t>((sq / 3) & 1));
         tcgen05_fence_after();
         const int kmax = T - kt * 128;
         auto emit = [&](const uint32_t* v, int c) {
@@ -286,7 +297,7 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
         }
         tmem_st_wait();
         tcgen05_fence_before();
-        mbar_arrive(&bar_p[g]);
+        mbar_arrive(&bar_p[sb]);
       }
       xsum[g * 128 + r] = sum;
       asm volatile("bar.sync 3, 256;" ::: "memory");
