@@ -1,21 +1,20 @@
 // Multi-tile non-causal attention on the 5th-gen tensor cores for sequences that do not fit one UMMA N:
 //   EVA ViT self-attention at 448 px, T = 1025 tokens, 16 heads x 88 - the resolution of every shipped reference config
 //   (configs/eval_configs/vqav2_eval_noise_0.yaml:35; eva_vit.py:123-153).
-// Head-major q, k, v ([B][H][T][hd], see attn_vit.cu).  Work unit = (sample, head, 128-query tile); keys in tiles of 128.
-// TMEM holds THREE S buffers of 128 x 128 fp32 (tile number modulo 3) and the O accumulator (128 x hd) - all of S (1025
-// columns) would not fit - so softmax is EXACT two-pass: pass 1 forms S = Q K^T tile by tile only for the row maximum, pass 2 forms it again,
-// turns it into P = exp2(s - max) in place (packed bf16, read back by the tensor core as the A operand of P.V) and
-// accumulates O += P V in TMEM across the key tiles: no online rescale of O, and the tensor pipe has the slack for the
-// second Q K^T (the kernel is MUFU-bound: 1025 exp2 per row).
-//   warp 0      TMA producer : Q tile, then the K / V tiles in consumption order through a 5-slot ring
-//   warp 1      MMA issuer   : S two tiles ahead of P.V (three S buffers), so a softmax group never waits for the tensor
-//                              core: with two buffers every S -> softmax -> P.V -> S hand-over (4 mbarrier round trips
-//                              per tile) sat on the critical path: 39k cycles per unit against 14k of MUFU + tensor work
-//   warps 4-7   softmax group 0: the EVEN key tiles;  warps 8-11  softmax group 1: the ODD key tiles (thread = query row);
-//               the two groups exchange row maximum and row sum through shared memory
+// Head-major q, k, v ([B][H][T][hd], see attn_vit.cu).  Work unit = (sample, head, PAIR of 128-query tiles); keys in tiles
+// of 128.  Softmax group g (4 warps, thread = query row) owns query tile 2 * pair + g with its own TMEM region
+// [S_g 128 columns | O_g hd columns]; BOTH groups consume every K / V tile from shared memory, so a tile is fetched from
+// L2 once per 256 query rows.  (The first version gave every 128-row unit its own pass over K and V: 32 GB of L2 -> SM
+// reads per layer at batch 256 = 6.1 TB/s, the chip's L2 bandwidth, and 5.3 ms - profiles/r02_ncu_kernels_summary.txt.)
+// All of S (1025 columns) does not fit TMEM, so softmax is EXACT two-pass: pass 1 forms S = Q K^T tile by tile only for
+// the row maximum, pass 2 forms it again, turns it into P = exp2(s - max) in place (packed bf16, read back by the tensor
+// core as the A operand of P.V) and accumulates O += P V in TMEM across the key tiles: no online rescale of O.
+//   warp 0      TMA producer : the pair's two Q tiles, then the K / V tiles in consumption order through a 4-slot ring
+//   warp 1      MMA issuer   : per key tile S_0, S_1 (pass 1, 2) and P_0.V, P_1.V (pass 2)
+//   warps 4-7   softmax group 0, warps 8-11 softmax group 1
 // The cls token is simply row 0 of the head block: tiles start at the block's first row, keys >= T are masked, rows >= T
 // are not stored (T = 1025 = 8 full tiles + 1 row; the specialised kernel in attn_vit.cu folds the cls row in on CUDA
-// cores instead, which pays off at T = 257 where a 129th tile would cost 2.25x).
+// cores instead, which pays off at T = 257 where a third tile would cost 2.25x).
 #include <stdlib.h>
 #include "common.cuh"
 #include "ops.h"
@@ -27,14 +26,16 @@ struct LongAttnParams {
   int H, hd, hd16, T;
   float scale_log2e;
   int n_tiles;                       // ceil(T / 128): key tiles = query tiles
-  int n_units;                       // B * H * n_tiles
+  int n_pairs;                       // ceil(n_tiles / 2): query-tile pairs per (sample, head)
+  int n_units;                       // B * H * n_pairs
   int pv_n;
+  int last_cols;                     // valid keys of the last key tile, rounded up to 16: its UMMA N and P.V depth
 };
 
 constexpr int LA_THREADS = 384;
 constexpr int LA_SUB = 16384;        // 128 rows x 128 B (one swizzle atom wide)
 constexpr int LA_TILE = 2 * LA_SUB;  // [cols 0..63 | cols 64..]
-constexpr int LA_STAGES = 5;
+constexpr int LA_STAGES = 4;
 constexpr int LA_OPITCH = 80;
 
 __device__ __forceinline__ uint64_t la_desc_mn(uint32_t addr, uint32_t lbo_bytes) {
@@ -59,26 +60,25 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
                  LongAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                               // one Q tile
-  uint8_t* ring = smem + LA_TILE;                   // LA_STAGES K / V tiles
+  uint8_t* sQ = smem;                               // two Q tiles (one per softmax group)
+  uint8_t* ring = smem + 2 * LA_TILE;               // LA_STAGES K / V tiles
   uint8_t* tail = ring + LA_STAGES * LA_TILE;
+  // every barrier is used in the same order by all its parties: use k has parity k & 1
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full = bars;                            // [STAGES] TMA -> MMA
   uint64_t* empty = bars + LA_STAGES;               // [STAGES] MMA -> TMA
-  uint64_t* bar_q = bars + 2 * LA_STAGES;           // Q tile landed
-  uint64_t* bar_qfree = bar_q + 1;                  // the unit's last S product retired: Q slot free
-  uint64_t* bar_s = bar_q + 2;                      // [3] S in buffer b
-  uint64_t* bar_sr = bar_q + 5;                     // [3] pass 1: buffer b read by its softmax group (128 arrivals)
-  uint64_t* bar_p = bar_q + 8;                      // [3] pass 2: P in buffer b (128 arrivals)
-  uint64_t* bar_pv = bar_q + 11;                    // [3] P.V out of buffer b retired
-  uint64_t* bar_o = bar_q + 14;                     // O of the unit complete
-  uint64_t* bar_ofree = bar_q + 15;                 // O drained by both groups (256 arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 16);
-  float* xch = reinterpret_cast<float*>(tail + 256);                 // [2 unit parities][2 groups][max | sum][128]
-  uint8_t* ostage = reinterpret_cast<uint8_t*>(xch + 2 * 2 * 2 * 128);   // [8 softmax warps][32 rows][LA_OPITCH]
+  uint64_t* bar_q = bars + 2 * LA_STAGES;           // both Q tiles landed
+  uint64_t* bar_qfree = bar_q + 1;                  // the unit's last S products retired: Q slots free
+  uint64_t* bar_s = bar_q + 2;                      // [2] S_g formed                     (once per tile of pass 1 and pass 2)
+  uint64_t* bar_sr = bar_q + 4;                     // [2] pass 1: S_g read by its group  (128 arrivals, once per pass-1 tile)
+  uint64_t* bar_p = bar_q + 6;                      // [2] pass 2: P_g written            (128 arrivals, once per pass-2 tile)
+  uint64_t* bar_o = bar_q + 8;                      // O of both groups complete (once per unit)
+  uint64_t* bar_ofree = bar_q + 9;                  // O drained by both groups (256 arrivals, once per unit)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 10);
+  uint8_t* ostage = tail + 256;                     // [8 softmax warps][32 rows][LA_OPITCH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hd = p.hd, T = p.T, n = p.n_tiles;
+  const int hd = p.hd, T = p.T, n = p.n_tiles, np = p.n_pairs;
   const int ksteps_s = p.hd16 / 16;
   const int grid = static_cast<int>(gridDim.x);
   const int first_unit = static_cast<int>(blockIdx.x);
@@ -89,8 +89,8 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
     tma_prefetch_desc(&map_k1); tma_prefetch_desc(&map_v0); tma_prefetch_desc(&map_v1);
     for (int i = 0; i < LA_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(bar_q, 1); mbar_init(bar_qfree, 1);
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(&bar_s[i], 1); mbar_init(&bar_sr[i], 128); mbar_init(&bar_p[i], 128); mbar_init(&bar_pv[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1); mbar_init(&bar_sr[i], 128); mbar_init(&bar_p[i], 128);
     }
     mbar_init(bar_o, 1); mbar_init(bar_ofree, 256);
     fence_barrier_init();
@@ -104,7 +104,7 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr uint32_t O_COL = 384;   // S buffers at columns 0, 128, 256
+  // TMEM region of group g: S_g (later P_g in its first 64 columns) at g * 256, O_g at g * 256 + 128
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -121,118 +121,130 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
       };
       int ui = 0;
       for (int u = first_unit; u < p.n_units; u += grid, ++ui) {
-        const int item = u / n, qt = u - item * n;
+        const int item = u / np, pr = u - item * np;
         const int row0 = item * T;
+        const int early = n < 2 ? n : 2;   // the first K tiles do not have to wait for the Q slots
+        for (int kt = 0; kt < early; ++kt) push(&map_k0, &map_k1, row0 + kt * 128);
         if (ui > 0) mbar_wait(bar_qfree, (ui - 1) & 1);
-        mbar_arrive_expect_tx(bar_q, tile_tx);
-        tma_load_2d(sQ, &map_q0, bar_q, 0, row0 + qt * 128);
-        tma_load_2d(sQ + LA_SUB, &map_q1, bar_q, 64, row0 + qt * 128);
-        for (int kt = 0; kt < n; ++kt) push(&map_k0, &map_k1, row0 + kt * 128);          // pass 1
-        for (int kt = 0; kt < n; ++kt) {                                                  // pass 2: K_kt, then V_{kt-2}
-          push(&map_k0, &map_k1, row0 + kt * 128);
-          if (kt >= 2) push(&map_v0, &map_v1, row0 + (kt - 2) * 128);
+        mbar_arrive_expect_tx(bar_q, 2 * tile_tx);
+        for (int g = 0; g < 2; ++g) {     // a second tile past the head block reads finite neighbour rows, never stored
+          tma_load_2d(sQ + g * LA_TILE, &map_q0, bar_q, 0, row0 + (2 * pr + g) * 128);
+          tma_load_2d(sQ + g * LA_TILE + LA_SUB, &map_q1, bar_q, 64, row0 + (2 * pr + g) * 128);
         }
-        if (n >= 2) push(&map_v0, &map_v1, row0 + (n - 2) * 128);
-        push(&map_v0, &map_v1, row0 + (n - 1) * 128);
+        for (int kt = early; kt < n; ++kt) push(&map_k0, &map_k1, row0 + kt * 128);      // pass 1: K
+        for (int kt = 0; kt < n; ++kt) {                                                  // pass 2: K_kt, V_kt
+          push(&map_k0, &map_k1, row0 + kt * 128);
+          push(&map_v0, &map_v1, row0 + kt * 128);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
+    // tcgen05.mma instructions of one thread execute in issue order, so an S product issued after the P.V that read the
+    // same TMEM columns needs no barrier; only the softmax groups' tcgen05.ld / st are waited for (bar_sr, bar_p).
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, 128);
+      const uint32_t idesc_s_last = make_idesc_bf16(128, p.last_cols);
       const uint32_t idesc_o = make_idesc_bf16(128, p.pv_n) | (1u << 16);   // B (= V) is MN-major
       int stage = 0;
       uint32_t phase = 0;
-      int n_s1[3] = {0, 0, 0}, n_pv[3] = {0, 0, 0};   // pass-1 uses / P.V uses of each S buffer so far
-      int last_kind[3] = {0, 0, 0};                  // 0 = never used, 1 = pass-1 tile, 2 = pass-2 tile
-      auto wait_free = [&](int b) {
-        if (last_kind[b] == 1) mbar_wait(&bar_sr[b], (n_s1[b] - 1) & 1);
-        else if (last_kind[b] == 2) mbar_wait(&bar_pv[b], (n_pv[b] - 1) & 1);
-      };
-      auto issue_s = [&](int b) {
-        mbar_wait(&full[stage], phase);
-        tcgen05_fence_after();
-        const uint8_t* sK = ring + stage * LA_TILE;
+      int n_sr[2] = {0, 0}, n_p[2] = {0, 0};   // per group: pass-1 tiles issued, pass-2 tiles whose P has been consumed
+      auto advance = [&]() { if (++stage == LA_STAGES) { stage = 0; phase ^= 1; } };
+      auto issue_s = [&](int g, const uint8_t* sK, bool last_tile) {
         for (int ks = 0; ks < ksteps_s; ++ks) {
-          const uint64_t ad = make_smem_desc_sw128(smem_u32(sQ + (ks >> 2) * LA_SUB)) + 2 * (ks & 3);
+          const uint64_t ad = make_smem_desc_sw128(smem_u32(sQ + g * LA_TILE + (ks >> 2) * LA_SUB)) + 2 * (ks & 3);
           const uint64_t bd = make_smem_desc_sw128(smem_u32(sK + (ks >> 2) * LA_SUB)) + 2 * (ks & 3);
-          umma_bf16(tmem_base + b * 128, ad, bd, idesc_s, ks != 0);
+          umma_bf16(tmem_base + g * 256, ad, bd, last_tile ? idesc_s_last : idesc_s, ks != 0);
         }
-        umma_commit(&empty[stage]);
-        umma_commit(&bar_s[b]);
-        if (++stage == LA_STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&bar_s[g]);
       };
       int ui = 0;
-      long long seq = 0;                             // S tiles issued so far (both passes, all units): buffer = seq % 3
       for (int u = first_unit; u < p.n_units; u += grid, ++ui) {
-        const long long seq2 = seq + n;              // sequence number of this unit's first pass-2 tile
-        auto issue_pv = [&](int j) {
-          const int b = static_cast<int>((seq2 + j) % 3);
-          mbar_wait(&bar_p[b], (n_pv[b]) & 1);
+        const int pr = u % np;
+        const int ng = (2 * pr + 1 < n) ? 2 : 1;      // the last pair of an odd tile count has one query tile
+        mbar_wait(bar_q, ui & 1);
+        // ---- pass 1: S only (row maximum)
+        for (int kt = 0; kt < n; ++kt) {
           mbar_wait(&full[stage], phase);
-          if (j == 0 && ui > 0) mbar_wait(bar_ofree, (ui - 1) & 1);     // the previous unit's O has been drained
-          tcgen05_fence_after();
-          const uint8_t* sV = ring + stage * LA_TILE;
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t bd = la_desc_mn(smem_u32(sV + ks * 16 * 128), LA_SUB);
-            umma_bf16_ts(tmem_base + O_COL, tmem_base + b * 128 + ks * 8, bd, idesc_o, (j | ks) != 0);
+          const uint8_t* sK = ring + stage * LA_TILE;
+          for (int g = 0; g < ng; ++g) {
+            if (kt > 0) mbar_wait(&bar_sr[g], (n_sr[g] - 1) & 1);   // the group has read the previous tile's scores
+            tcgen05_fence_after();
+            issue_s(g, sK, kt == n - 1);
+            ++n_sr[g];
           }
           umma_commit(&empty[stage]);
-          umma_commit(&bar_pv[b]);
-          ++n_pv[b];
-          if (++stage == LA_STAGES) { stage = 0; phase ^= 1; }
-        };
-        mbar_wait(bar_q, ui & 1);
-        for (int kt = 0; kt < n; ++kt, ++seq) {       // pass 1: S only (row maximum)
-          const int b = static_cast<int>(seq % 3);
-          wait_free(b);
-          issue_s(b);
-          ++n_s1[b];
-          last_kind[b] = 1;
+          advance();
         }
-        for (int kt = 0; kt < n; ++kt, ++seq) {       // pass 2: S again, P.V two tiles behind
-          const int b = static_cast<int>(seq % 3);
-          wait_free(b);
-          issue_s(b);
-          last_kind[b] = 2;
-          if (kt == n - 1) umma_commit(bar_qfree);    // the unit's last read of the Q tile
-          if (kt >= 2) issue_pv(kt - 2);
+        // ---- pass 2: S_g(0); then per key tile P_g(kt).V followed at once by S_g(kt + 1)
+        mbar_wait(&full[stage], phase);
+        for (int g = 0; g < ng; ++g) {
+          mbar_wait(&bar_sr[g], (n_sr[g] - 1) & 1);
+          tcgen05_fence_after();
+          issue_s(g, ring + stage * LA_TILE, n == 1);
         }
-        if (n >= 2) issue_pv(n - 2);
-        issue_pv(n - 1);
+        if (n == 1) umma_commit(bar_qfree);
+        umma_commit(&empty[stage]);
+        advance();
+        for (int kt = 0; kt < n; ++kt) {
+          const bool more = kt + 1 < n;
+          const int sv = stage;
+          mbar_wait(&full[sv], phase);                // V_kt
+          advance();
+          const int sk = stage;
+          if (more) { mbar_wait(&full[sk], phase); advance(); }   // K_{kt+1}
+          if (kt == 0 && ui > 0) mbar_wait(bar_ofree, (ui - 1) & 1);   // the previous unit's O has been drained
+          const uint8_t* sV = ring + sv * LA_TILE;
+          const int pv_steps = (kt == n - 1) ? p.last_cols / 16 : 8;
+          for (int g = 0; g < ng; ++g) {
+            mbar_wait(&bar_p[g], n_p[g] & 1);
+            ++n_p[g];
+            tcgen05_fence_after();
+            for (int ks = 0; ks < pv_steps; ++ks) {
+              const uint64_t bd = la_desc_mn(smem_u32(sV + ks * 16 * 128), LA_SUB);
+              umma_bf16_ts(tmem_base + g * 256 + 128, tmem_base + g * 256 + ks * 8, bd, idesc_o, (kt | ks) != 0);
+            }
+            if (g == ng - 1) umma_commit(&empty[sv]);
+            if (more) issue_s(g, ring + sk * LA_TILE, kt + 1 == n - 1);
+          }
+          if (more) {
+            if (kt + 1 == n - 1) umma_commit(bar_qfree);   // the unit's last read of the Q tiles
+            umma_commit(&empty[sk]);
+          }
+        }
         umma_commit(bar_o);
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax groups, thread = query row
-    const int g = (warp - 4) >> 2;                    // group g owns the key tiles kt = g, g + 2, ...
-    const int r = (warp & 3) * 32 + lane;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const uint32_t t_o = t_lane + O_COL;
+    const int g = (warp - 4) >> 2;                    // group g owns query tile 2 * pair + g
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * 256;
+    const uint32_t t_o = t_s + 128;
     uint8_t* patch = ostage + (warp - 4) * (32 * LA_OPITCH);
+    int cnt_s = 0;                                    // uses of bar_s[g] so far
     int ui = 0;
     for (int u = first_unit; u < p.n_units; u += grid, ++ui) {
-      const int item = u / n, qt = u - item * n;
+      const int item = u / np, pr = u - item * np;
+      const int qt = 2 * pr + g;
       const int h = item % p.H, bb = item / p.H;
-      float* xmax = xch + (ui & 1) * 512;             // [2 groups][128]
-      float* xsum = xmax + 256;
-      // ---- pass 1: row maximum over this group's key tiles
-      // S tile number of this unit's pass-1 tile 0 (2n tiles per unit): buffer = number % 3, its use number / 3
-      const long long seq1 = static_cast<long long>(ui) * 2 * n;
+      if (qt >= n) {                                  // odd tile count: the last pair has no second query tile
+        mbar_arrive(bar_ofree);
+        continue;
+      }
+      // ---- pass 1: row maximum
       float mx = -INFINITY;
-      for (int kt = g; kt < n; kt += 2) {
-        const long long sq = seq1 + kt;
-        const int sb = static_cast<int>(sq % 3);
-        const uint32_t t_s = t_lane + sb * 128;
-        mbar_wait(&bar_s[sb], static_cast<uint32_t>((sq / 3) & 1));
+      for (int kt = 0; kt < n; ++kt) {
+        mbar_wait(&bar_s[g], cnt_s & 1);
+        ++cnt_s;
         tcgen05_fence_after();
         const int kmax = T - kt * 128;                // keys [0, kmax) of this tile exist
+        const int ncols = kt == n - 1 ? p.last_cols : 128;   // columns the tensor core wrote
         uint32_t va[16], vb[16];
         tmem_ld_x16(t_s, va);
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = 0; c < ncols; c += 32) {
           tmem_ld_wait();
-          tmem_ld_x16(t_s + c + 16, vb);
+          if (c + 16 < ncols) tmem_ld_x16(t_s + c + 16, vb);
           if (c + 16 <= kmax) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
@@ -240,8 +252,9 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 16; ++i) if (c + i < kmax) mx = fmaxf(mx, __uint_as_float(va[i]));
           }
+          if (c + 16 >= ncols) break;
           tmem_ld_wait();
-          if (c + 32 < 128) tmem_ld_x16(t_s + c + 32, va);
+          if (c + 32 < ncols) tmem_ld_x16(t_s + c + 32, va);
           if (c + 32 <= kmax) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
@@ -251,20 +264,15 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
           }
         }
         tcgen05_fence_before();
-        mbar_arrive(&bar_sr[sb]);
+        mbar_arrive(&bar_sr[g]);
       }
-      xmax[g * 128 + r] = mx;
-      asm volatile("bar.sync 3, 256;" ::: "memory");
-      mx = fmaxf(xmax[r], xmax[128 + r]);
       if (mx == -INFINITY) mx = 0.f;
       const float neg_ms = -mx * p.scale_log2e;
-      // ---- pass 2: P = exp2(s * scale - max * scale), packed bf16 in place over the first 64 columns of the buffer
+      // ---- pass 2: P = exp2(s * scale - max * scale), packed bf16 in place over the first 64 columns of S_g
       float sum = 0.f;
-      for (int kt = g; kt < n; kt += 2) {
-        const long long sq = seq1 + n + kt;
-        const int sb = static_cast<int>(sq % 3);
-        const uint32_t t_s = t_lane + sb * 128;
-        mbar_wait(&bar_s[sb], static_cast<uint32_t>((sq / 3) & 1));
+      for (int kt = 0; kt < n; ++kt) {
+        mbar_wait(&bar_s[g], cnt_s & 1);
+        ++cnt_s;
         tcgen05_fence_after();
         const int kmax = T - kt * 128;
         auto emit = [&](const uint32_t* v, int c) {
@@ -284,34 +292,31 @@ attn_long_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_consta
           for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
           tmem_st_x8(t_s + (c >> 1), w);
         };
+        const int ncols = kt == n - 1 ? p.last_cols : 128;
         uint32_t va[16], vb[16];
         tmem_ld_x16(t_s, va);
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = 0; c < ncols; c += 32) {
           tmem_ld_wait();
-          tmem_ld_x16(t_s + c + 16, vb);
+          if (c + 16 < ncols) tmem_ld_x16(t_s + c + 16, vb);
           emit(va, c);
+          if (c + 16 >= ncols) break;
           tmem_ld_wait();
-          if (c + 32 < 128) tmem_ld_x16(t_s + c + 32, va);
+          if (c + 32 < ncols) tmem_ld_x16(t_s + c + 32, va);
           emit(vb, c + 16);
         }
         tmem_st_wait();
         tcgen05_fence_before();
-        mbar_arrive(&bar_p[sb]);
+        mbar_arrive(&bar_p[g]);
       }
-      xsum[g * 128 + r] = sum;
-      asm volatile("bar.sync 3, 256;" ::: "memory");
-      sum = xsum[r] + xsum[128 + r];
-      // ---- epilogue: O / rowsum -> bf16 -> shared-memory transpose -> global; 32-column groups alternate between the groups
+      // ---- epilogue: O_g / rowsum -> bf16 -> shared-memory transpose -> global
       mbar_wait(bar_o, ui & 1);
       tcgen05_fence_after();
       const float inv = sum > 0.f ? 1.f / sum : 0.f;
       const int q_warp0 = qt * 128 + (warp & 3) * 32;
       __nv_bfloat16* obase = p.o + (static_cast<long long>(bb) * T + q_warp0) * p.ldo + h * hd;
-      int grp = 0;
 #pragma unroll 1
-      for (int c = 0; c < hd; c += 32, ++grp) {
-        if ((grp & 1) != g) continue;                 // warp-uniform
+      for (int c = 0; c < hd; c += 32) {
         uint32_t v[32];
         tmem_ld_x32(t_o + c, v);
         tmem_ld_wait();
@@ -385,7 +390,7 @@ int attn_long_supported(const cgpt_attn_args* a) {
   if (a->head_dim <= 64 || a->head_dim > 128 || (a->head_dim & 7)) return 0;
   if (a->Tq != a->Tk || a->q_rows_per_batch != a->Tq || a->kv_rows_per_batch != a->Tk || a->Tk < 1) return 0;
   if (a->B * (long long)a->H * a->Tk > 0x7fffffffLL) return 0;
-  if (a->B * (long long)a->H * ((a->Tk + 127) / 128) > 0x7fffffffLL) return 0;
+  if (a->B * (long long)a->H * ((a->Tk + 255) / 256) > 0x7fffffffLL) return 0;
   if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
        reinterpret_cast<uintptr_t>(a->o)) & 15)
     return 0;
@@ -400,15 +405,17 @@ int attention_long(const cgpt_attn_args* a, cudaStream_t stream) {
   p.H = a->H; p.hd = a->head_dim; p.hd16 = (a->head_dim + 15) & ~15; p.T = a->Tk;
   p.scale_log2e = a->scale * 1.4426950408889634f;
   p.n_tiles = (a->Tk + 127) / 128;
-  p.n_units = a->B * a->H * p.n_tiles;
+  p.n_pairs = (p.n_tiles + 1) / 2;
+  p.n_units = a->B * a->H * p.n_pairs;
   p.pv_n = p.hd16;
+  p.last_cols = ((a->Tk - (p.n_tiles - 1) * 128) + 15) & ~15;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int smem = (1 + LA_STAGES) * LA_TILE + 256 + 2 * 2 * 2 * 128 * 4 + 8 * 32 * LA_OPITCH + 1024;
+  const int smem = (2 + LA_STAGES) * LA_TILE + 256 + 8 * 32 * LA_OPITCH + 1024;
   const long long rows = (long long)a->B * a->H * a->Tk;
   const int c1 = p.hd16 - 64;
   CUtensorMap mq0, mq1, mk0, mk1, mv0, mv1;
