@@ -181,9 +181,38 @@ def test_head_major_rejects_unsupported_shapes(lib):
     (2, 3, 258, 96),        # just past the one-tile kernel's range
     (2, 2, 640, 128),       # 5 full tiles, hd = 128
     (5, 4, 513, 72),        # odd tile count, one-row last tile, hd = 72
+    (2, 3, 360, 88),        # last tile of 104 keys: both 64-key halves exist, the second one ragged (40 keys)
+    (1, 2, 512, 88),        # even tile count: both softmax groups busy in every unit
+    (2, 2, 321, 80),        # last tile of 65 keys: the second half holds one key
 ])
 def test_head_major_multi_tile_kernel(lib, B, H, T, hd):
     _run_head_major(lib, B, H, T, hd, seed=T + hd)
+
+
+@pytest.mark.parametrize("where", ["first", "middle", "last"])
+def test_multi_tile_kernel_rescales_when_the_row_maximum_jumps(lib, where):
+    """The multi-tile kernel runs an online softmax with a lazy rescale of O (attn_long.cu): plant keys whose scores tower
+    over everything before them so that the running maximum jumps by far more than the rescale threshold at a chosen key
+    tile - at the very end the previously accumulated O is scaled by ~2^-60 and the result is the planted key's value."""
+    B, H, T, hd = 2, 3, 1025, 88
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q, k, v = (torch.randn(B, H, T, hd, device="cuda", generator=g).bfloat16() for _ in range(3))
+    pos = {"first": 5, "middle": 600, "last": T - 1}[where]
+    # key `pos` is aligned with every query of head 1 (score ~ +24, the rest stay within +-3), and mildly with those of head 2
+    k[:, 1, pos] = 4.0
+    q[:, 1] = (q[:, 1].float().abs() * 0.5 + 0.25).bfloat16()
+    k[:, 2, pos] = (k[:, 2, pos].float() * 4).bfloat16()
+    out = torch.full((B * T, H * hd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    scale = hd ** -0.5
+    lib.attention(q.view(-1), k.view(-1), v.view(-1), out, B=B, H=H, Tq=T, Tk=T, head_dim=hd, scale=scale, head_major=True)
+    torch.cuda.synchronize()
+    s = (q.float() @ k.float().transpose(-1, -2)) * scale
+    assert (s[:, 1, :, pos] - s[:, 1].amax(-1)).abs().max().item() == 0.0     # the planted key holds every row's maximum
+    assert (s[:, 1, :, pos] - s[:, 1, :, :pos].amax(-1)).min().item() > 8.0        # a jump of > 11 in log2 units
+    ref = (s.softmax(-1) @ v.float()).transpose(1, 2).reshape(B * T, H * hd)
+    assert not torch.isnan(out.float()).any()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"max err {err}"
 
 
 def test_multi_tile_kernel_many_units_and_determinism(lib):
