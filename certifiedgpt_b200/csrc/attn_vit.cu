@@ -90,7 +90,8 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
   constexpr int OPITCH = 80;                           // bytes per staged row: 32 bf16 + 16 B pad (conflict-free 16-byte writes)
   uint8_t* ostage = reinterpret_cast<uint8_t*>(xo + 5 * 96 + 32);   // [8 softmax warps][32 rows][OPITCH]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index and TMEM base through a lane-0 shuffle: known warp-uniform to the compiler (see the MMA issuer)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 #define VA_STAMP(slot) do { if (p.dbg) p.dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
   const int hd = p.hd, E = p.E, T = p.T, nqt = p.n_qtiles;
   const int Tk_main = T - E, Tq_main = T - E;
@@ -163,7 +164,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -189,8 +190,12 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0 && n_mine > 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    // The whole warp walks the loop and elect.sync picks the issuing lane: with warp-uniform control flow the UMMA
+    // operands stay in uniform registers and UTCHMMA issues back to back.  Under `if (lane == 0)` every operand went
+    // through R2UR inside an ELECT loop, 100-170 cycles per MMA (profiles/r02_attn_long_probe.txt) - three times what
+    // the 48-cycle P.V MMAs take.
+    if (n_mine > 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, p.nk_pad);
       const uint32_t idesc_o = make_idesc_bf16(128, p.pv_n) | (1u << 16);   // B (= V) is MN-major
       auto issue_s = [&](int t) {
@@ -198,18 +203,18 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
         for (int ks = 0; ks < ksteps_s; ++ks) {
           const uint64_t ad = va_desc_kmajor(smem_u32(sQ + t * 2 * VSUB + (ks >> 2) * VSUB)) + 2 * (ks & 3);
           const uint64_t bd = va_desc_kmajor(smem_u32(sK + (ks >> 2) * kv_sub)) + 2 * (ks & 3);
-          umma_bf16(d_tmem, ad, bd, idesc_s, ks != 0);
+          if (elect_one()) umma_bf16(d_tmem, ad, bd, idesc_s, ks != 0);
         }
-        umma_commit(&bar_s[t]);
+        if (elect_one()) umma_commit(&bar_s[t]);
       };
       auto issue_pv = [&](int t) {
         const uint32_t d_tmem = tmem_base + t * 256 + 128;
         const uint32_t a_tmem = tmem_base + t * 256;       // P_t: 8 columns (16 bf16) per K step
         for (int ks = 0; ks < ksteps_o; ++ks) {
           const uint64_t bd = va_desc_mnmajor(smem_u32(sV + ks * 16 * 128), static_cast<uint32_t>(kv_sub));
-          umma_bf16_ts(d_tmem, a_tmem + ks * 8, bd, idesc_o, ks != 0);
+          if (elect_one()) umma_bf16_ts(d_tmem, a_tmem + ks * 8, bd, idesc_o, ks != 0);
         }
-        umma_commit(&bar_o[t]);
+        if (elect_one()) umma_commit(&bar_o[t]);
       };
       mbar_wait(bar_k, 0);
       for (int t = 0; t < nqt; ++t) {
@@ -217,7 +222,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
         tcgen05_fence_after();
         issue_s(t);
       }
-      VA_STAMP(2);
+      if (lane == 0) VA_STAMP(2);
       // both softmax groups run in lockstep (same item, same phase), so the natural order is fixed:
       // P.V of both tiles as their P arrives, then S of the next item for each tile as its region drains
       for (int it = 0; it < n_mine; ++it) {
@@ -238,7 +243,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constan
           }
         }
       }
-      VA_STAMP(3);
+      if (lane == 0) VA_STAMP(3);
     }
   } else if (warp == 2 || warp == 3) {
     // ------------------------------------------------------------------ cls query row, CUDA cores
