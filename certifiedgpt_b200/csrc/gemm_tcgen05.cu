@@ -37,13 +37,20 @@ constexpr int EPI_WARPS = 8;
 // CTAS = 1: one CTA owns a 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, cta_group::2) owns a
 // 256 x BN tile; each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), so shared
 // memory write (TMA) and read (UMMA) traffic per SM drops by a third and L2->SM traffic by a third.
-template <int BN, int CTAS>
+// MT = 2 (CTA pairs only): each CTA owns TWO 128-row sub-tiles of A that share one B tile - a 512 x BN tile per pair, both
+// TMEM accumulator stages belong to the same tile (no epilogue / mainloop overlap across tiles).  A third less L2 -> SM
+// traffic and fewer DRAM re-reads per FLOP; k-blocks of 64 so that four 48 KB stages fit.  This is cuBLAS's own tiling
+// for these shapes (nvjet 256x256 per CTA, 2cta; profiles/r02_gemm_vs_cublas.txt): the step runs at the 1 kW power cap,
+// where bytes moved per FLOP decide the throughput and an exposed epilogue only lets the clock rise.
+template <int BN, int CTAS, int MT = 1>
 struct GemmCfg {
+  static constexpr int BK_ = MT == 2 ? 64 : BK;          // k-block of a pipeline stage
+  static constexpr int KSUB_ = BK_ / BKA;
   static constexpr int A_SUB = BM * BKA * 2;             // one [128 x 64] sub-tile
-  static constexpr int A_BYTES = A_SUB * KSUB;
+  static constexpr int A_BYTES = A_SUB * KSUB_ * MT;
   static constexpr int B_ROWS = BN / CTAS;
   static constexpr int B_SUB = B_ROWS * BKA * 2;
-  static constexpr int B_BYTES = B_SUB * KSUB;
+  static constexpr int B_BYTES = B_SUB * KSUB_;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int RED_STAGE_BYTES = 8 * 32 * 20 * 4;   // 8 epilogue warps x [32 rows][16 + 4 pad] fp32
@@ -51,6 +58,7 @@ struct GemmCfg {
                                     RED_STAGE_BYTES + 2 * 32 * 8 /*head-major column offsets*/;
   static_assert(B_SUB % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
   static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
+  static_assert(MT == 1 || (MT == 2 && CTAS == 2 && BN == 256), "two M sub-tiles per CTA: CTA pairs with 256-wide tiles only");
 };
 
 struct EpiParams {
@@ -410,12 +418,13 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
 // Each special epilogue is its own instantiation so that the hot epilogue loop of the common kernel keeps the code size
 // it was tuned at (the GELU GEMM lost 19 % when two more branches were compiled into it: instruction cache).
 constexpr int MODE_PLAIN = 0, MODE_ROPE = 1, MODE_HM = 2, MODE_RMW = 3;
-template <int BN, int CTAS, int MODE = MODE_PLAIN>
+template <int BN, int CTAS, int MODE = MODE_PLAIN, int MT = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
                          EpiParams epi) {
-  using Cfg = GemmCfg<BN, CTAS>;
+  using Cfg = GemmCfg<BN, CTAS, MT>;
+  constexpr int BKC = Cfg::BK_, KSUBC = Cfg::KSUB_;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array: a round trip through uintptr_t would
@@ -438,10 +447,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   // a "tile" is (BM*CTAS) x BN; with CTAS = 2 both CTAs of the pair walk the same tile sequence
   const int cta_rank = CTAS == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const int worker = blockIdx.x / CTAS, num_workers = gridDim.x / CTAS;
-  const int m_tiles = (M + BM * CTAS - 1) / (BM * CTAS);
+  const int m_tiles = (M + BM * CTAS * MT - 1) / (BM * CTAS * MT);
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int num_kb = (K + BK - 1) / BK;
+  const int num_kb = (K + BKC - 1) / BKC;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -477,27 +486,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         int m_blk, n_blk;
         tile_coords(tile, m_tiles, n_tiles, epi.group_m, m_blk, n_blk);
-        m_blk = m_blk * CTAS + cta_rank;
+        // 128-row block of sub-tile mt of this CTA: ((m_tile * MT + mt) * CTAS + cta_rank)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (CTAS == 2) {
             // the leader's barrier collects the bytes of BOTH CTAs' loads
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
 #pragma unroll
-            for (int sub = 0; sub < KSUB; ++sub) {
-              tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES + sub * Cfg::A_SUB, &tma_a, &full_bar[stage],
-                              kb * BK + sub * BKA, m_blk * BM);
+            for (int sub = 0; sub < KSUBC; ++sub) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt)
+                tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES + (mt * KSUBC + sub) * Cfg::A_SUB, &tma_a, &full_bar[stage],
+                                kb * BKC + sub * BKA, ((m_blk * MT + mt) * CTAS + cta_rank) * BM);
               tma_load_2d_2sm(smem_b + stage * Cfg::B_BYTES + sub * Cfg::B_SUB, &tma_b, &full_bar[stage],
-                              kb * BK + sub * BKA, n_blk * BN + cta_rank * Cfg::B_ROWS);
+                              kb * BKC + sub * BKA, n_blk * BN + cta_rank * Cfg::B_ROWS);
             }
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
-            for (int sub = 0; sub < KSUB; ++sub) {
+            for (int sub = 0; sub < KSUBC; ++sub) {
               tma_load_2d(smem_a + stage * Cfg::A_BYTES + sub * Cfg::A_SUB, &tma_a, &full_bar[stage],
-                          kb * BK + sub * BKA, m_blk * BM);
+                          kb * BKC + sub * BKA, (m_blk * CTAS + cta_rank) * BM);
               tma_load_2d(smem_b + stage * Cfg::B_BYTES + sub * Cfg::B_SUB, &tma_b, &full_bar[stage],
-                          kb * BK + sub * BKA, n_blk * BN);
+                          kb * BKC + sub * BKA, n_blk * BN);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -515,10 +526,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       long long t_wait_epi = 0, t_wait_tma = 0, t_total0 = clock64();
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         long long c0 = clock64();
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (MT == 2) { mbar_wait(&tmem_empty[0], acc_phase ^ 1); mbar_wait(&tmem_empty[1], acc_phase ^ 1); }
+        else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         t_wait_epi += clock64() - c0;
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t d_tmem = tmem_base + (MT == 2 ? 0 : acc * 256);
         for (int kb = 0; kb < num_kb; ++kb) {
           c0 = clock64();
           mbar_wait(&full_bar[stage], phase);
@@ -527,18 +539,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
+          for (int k = 0; k < BKC / UMMA_K; ++k) {
             // sub-tile (k / 4) of the stage, then 16 bf16 = 32 B inside the 128B swizzle atom (+2 in addr>>4 units)
-            const uint64_t ad = adesc + (k >> 2) * (Cfg::A_SUB >> 4) + 2 * (k & 3);
             const uint64_t bd = bdesc + (k >> 2) * (Cfg::B_SUB >> 4) + 2 * (k & 3);
-            if (CTAS == 2) umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
-            else           umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {      // the M sub-tiles of the tile share the B operand; accumulator mt
+              const uint64_t ad = adesc + (mt * KSUBC + (k >> 2)) * (Cfg::A_SUB >> 4) + 2 * (k & 3);
+              if (CTAS == 2) umma_bf16_2sm(d_tmem + mt * 256, ad, bd, idesc, (kb | k) != 0);
+              else           umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            }
           }
           if (CTAS == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (CTAS == 2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (MT == 2) {
+          umma_commit_2sm(&tmem_full[0]);
+          umma_commit_2sm(&tmem_full[1]);
+          acc_phase ^= 1;
+        } else {
+          if (CTAS == 2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
       }
       if (epi.dbg) {
         epi.dbg[blockIdx.x * 8 + 0] = t_wait_epi;
@@ -556,10 +577,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     int acc = 0;
     uint32_t acc_phase = 0;
     long long t_wait_mma = 0, t_work = 0, t_bar = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers)
+    for (int mt = 0; mt < MT; ++mt) {          // MT = 2: accumulator stage mt holds the tile's M sub-tile mt
       int m_blk, n_blk;
       tile_coords(tile, m_tiles, n_tiles, epi.group_m, m_blk, n_blk);
-      m_blk = m_blk * CTAS + cta_rank;
+      m_blk = (m_blk * MT + mt) * CTAS + cta_rank;
       const int n_base = n_blk * BN;
       float* bias_s = bias_smem + acc * 256;
       long long c0 = clock64();
@@ -691,17 +713,17 @@ struct GemmProfRec { cudaEvent_t e0, e1; int M, N, K; };
 static std::deque<GemmProfRec> g_prof;
 static bool g_prof_on = false;
 
-template <int BN, int CTAS, int MODE = MODE_PLAIN>
+template <int BN, int CTAS, int MODE = MODE_PLAIN, int MT = 1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                        const EpiParams& epi, int max_ctas, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CTAS>;
+  using Cfg = GemmCfg<BN, CTAS, MT>;
   static bool configured = false;
   if (!configured) {
-    CGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS, MODE>,
+    CGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS, MODE, MT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int tiles = ((M + BM * CTAS - 1) / (BM * CTAS)) * ((N + BN - 1) / BN);
+  const int tiles = ((M + BM * CTAS * MT - 1) / (BM * CTAS * MT)) * ((N + BN - 1) / BN);
   int workers = g_num_sms / CTAS;
   if (max_ctas > 0 && workers > max_ctas / CTAS) workers = max_ctas / CTAS > 0 ? max_ctas / CTAS : 1;
   if (tiles < workers) workers = tiles;
@@ -717,7 +739,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS, MODE>, ta, tb, M, N, K, epi));
+  CGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS, MODE, MT>, ta, tb, M, N, K, epi));
   ++g_gemm_launches;
   return 0;
 }
@@ -861,15 +883,29 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
     }
   }
   int rc = 0;
+  // 512 x 256 tiles per CTA pair (two M sub-tiles per CTA sharing the B tile) for the longest K only (Llama down, K = 11008:
+  // 1185 -> 1282 TFLOP/s sustained; its DRAM over-read was the worst).  At K = 4096 / 6144 the epilogue this tiling
+  // exposes costs more than the saved operand traffic gives back (-4..-7 %, profiles/r02_gemm_vs_cublas.txt); cuBLAS
+  // affords the same tiling everywhere with a TMA-store epilogue.  CGPT_GEMM_MT = 1 / 2 forces one form.
+  const char* mt_env = getenv("CGPT_GEMM_MT");      // read per call: the tests switch it inside one process
+  const int mt_forced = mt_env ? atoi(mt_env) : 0;
+  const bool big = ctas == 2 && bn == 256 && M >= 4096 && (mt_forced == 2 || (mt_forced == 0 && K >= 8192));
+  if (big) p.group_m = p.group_m > 1 ? p.group_m / 2 : 1;
+  // the 512-row tiles expose their epilogue: take the faster, sector-coalesced form of the in-place residual reductions
+  // (llama_down sustained: 1217 -> 1267 TFLOP/s; with 256-row tiles the two forms tie, scripts/gemm_down_probe.py)
+  if (big && p.red_inplace == 1 && p.ldo % 4 == 0 && !getenv("CGPT_GEMM_RED_DIRECT")) p.red_inplace = 2;
   if (rp != nullptr) {
     CGPT_REQUIRE(bn == 256, "gemm(rope): needs 256-wide N tiles (got %d)", bn);
-    rc = ctas == 2 ? launch_gemm<256, 2, MODE_ROPE>(ta, tb, M, N, K, p, e->max_ctas, stream)
+    rc = big ? launch_gemm<256, 2, MODE_ROPE, 2>(ta, tb, M, N, K, p, e->max_ctas, stream)
+       : ctas == 2 ? launch_gemm<256, 2, MODE_ROPE>(ta, tb, M, N, K, p, e->max_ctas, stream)
                    : launch_gemm<256, 1, MODE_ROPE>(ta, tb, M, N, K, p, e->max_ctas, stream);
   } else if (p.hm_T > 0) {
     rc = ctas == 2 ? launch_gemm<256, 2, MODE_HM>(ta, tb, M, N, K, p, e->max_ctas, stream)
                    : launch_gemm<256, 1, MODE_HM>(ta, tb, M, N, K, p, e->max_ctas, stream);
   } else if (p.red_inplace == 3) {
     rc = launch_gemm<256, 2, MODE_RMW>(ta, tb, M, N, K, p, e->max_ctas, stream);
+  } else if (big) {
+    rc = launch_gemm<256, 2, MODE_PLAIN, 2>(ta, tb, M, N, K, p, e->max_ctas, stream);
   } else
   switch (bn * 10 + ctas) {
     case 2561: rc = launch_gemm<256, 1>(ta, tb, M, N, K, p, e->max_ctas, stream); break;

@@ -77,6 +77,48 @@ def test_gemm_patch_embed_epilogue(lib):
     assert (got[:, 0] == 0).all()
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 4096),      # 8 full 512-row tiles x 2 n-tiles
+                                   (5000, 768, 4160),      # ragged last m-tile (392 of 512 rows), ragged K (65 k-blocks of 64)
+                                   (4500, 1408, 6144),     # ViT fc2 shape class, masked last n-tile
+                                   (4100, 4096, 11008)])   # Llama down: 172 k-blocks; last m-tile holds 4 rows
+def test_gemm_512_row_tiles_for_long_k(lib, M, N, K):
+    """The 512 x 256 tile per CTA pair (two M sub-tiles per CTA sharing the B tile, both TMEM accumulator stages inside one
+    tile; the default for K >= 8192, forced here for every shape): plain, bias + GELU, SwiGLU, bf16 residual and the in-place
+    fp32 residual update, and the same bits as the 256-row tiles."""
+    import os
+    os.environ["CGPT_GEMM_MT"] = "2"
+    try:
+        _check_512_row_tiles(lib, M, N, K)
+    finally:
+        os.environ.pop("CGPT_GEMM_MT", None)
+
+
+def _check_512_row_tiles(lib, M, N, K):
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    _close(lib.gemm(a, w), _ref(a, w))
+    _close(lib.gemm(a, w, bias=bias, act=lib.ACT_GELU), _ref(a, w, bias, act=1))
+    _close(lib.gemm(a, w, act=lib.ACT_SWIGLU), _ref(a, w, act=2), tol=2e-2)
+    resid = torch.randn(M, N, device="cuda")
+    y = lib.gemm(a, w, bias=bias, resid=resid, out_dtype=torch.float32)
+    assert torch.allclose(y, _ref(a, w, bias, resid=resid), atol=1e-3, rtol=1e-5)
+    r2 = resid.clone()
+    lib.gemm(a, w, bias=bias, resid=r2, out=r2)                    # red.global.add epilogue
+    assert torch.allclose(r2, y, atol=1e-3, rtol=1e-5)
+    rb = resid.bfloat16()
+    _close(lib.gemm(a, w, bias=bias, resid=rb), _ref(a, w, bias, resid=rb))
+    # same bits whatever the tile and the number of CTAs: every output is accumulated in the same k order
+    import os
+    y2 = lib.gemm(a, w, bias=bias)
+    assert torch.equal(y2, lib.gemm(a, w, bias=bias, max_ctas=2))
+    os.environ["CGPT_GEMM_MT"] = "1"                               # the 256-row tiles every other shape uses
+    y1 = lib.gemm(a, w, bias=bias)
+    os.environ["CGPT_GEMM_MT"] = "2"
+    assert torch.equal(y1, y2)
+
+
 def test_gemm_rejects_bad_shapes(lib):
     a = torch.zeros(8, 12, device="cuda", dtype=torch.bfloat16)
     w = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)
