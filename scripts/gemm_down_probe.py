@@ -1,6 +1,6 @@
-"""Sustained throughput of the Llama down projection with its in-place fp32 residual epilogue (M = 79 200, N = 4096,
-K = 11008) under the tile / epilogue switches: CGPT_GEMM_MT (1 = 256-row tiles, 2 = 512-row tiles) x direct / coalesced
-red.global.add form.  usage: python scripts/gemm_down_probe.py"""
+"""Sustained throughput of a residual GEMM with its in-place fp32 residual epilogue (llama_down: M = 79 200, N = 4096,
+K = 11008; llama_o; vit_fc2) under the tile / epilogue switches: CGPT_GEMM_MT (1 = 256-row tiles, 2 = 512-row tiles) x direct / coalesced
+red.global.add form.  usage: python scripts/gemm_down_probe.py [llama_down | llama_o | vit_fc2]"""
 import os
 import sys
 import time
@@ -10,7 +10,9 @@ import torch
 
 from certifiedgpt_b200 import _lib as L
 
-M, N, K = 1100 * 72, 4096, 11008
+SHAPES = {"llama_down": (1100 * 72, 4096, 11008), "llama_o": (1100 * 72, 4096, 4096), "vit_fc2": (1100 * 257, 1408, 6144)}
+name = sys.argv[1] if len(sys.argv) > 1 else "llama_down"
+M, N, K = SHAPES[name]
 a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
 w = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
 res = torch.zeros(M, N, device="cuda", dtype=torch.float32)
@@ -46,4 +48,4 @@ for rep in range(2):
             if form == "coalesced":
                 os.environ["CGPT_GEMM_RED_COALESCED"] = "1"
             ms = window()
-            print(f"llama_down + fp32 residual, {256 * int(mt)}-row tiles, {form:9s} reductions: {ms:.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
+            print(f"{name} + fp32 residual, {256 * int(mt)}-row tiles, {form:9s} reductions: {ms:.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
