@@ -1,9 +1,8 @@
 #!/bin/bash
-# round-2 GPU call 11: memcheck of the attention kernels, whole suite, final 1-GPU bench line and the reference arm
+# round-2 GPU call 11: whole suite, final 1-GPU bench line and the reference arm
 O=gpurun_out
 mkdir -p $O
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_attention_gpu.py -q -x -k "multi_tile or head_major" > $O/r2_c11_memcheck.log 2>&1
-echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed" $O/r2_c11_memcheck.log | tail -3
+# (compute-sanitizer is closed on this pool: the memcheck pass planned here could not run)
 timeout 1500 python -m pytest tests -m gpu -q > $O/r2_c11_tests.log 2>&1
 echo "suite rc=$?"; grep -E "passed|failed" $O/r2_c11_tests.log | tail -3; grep -n "^FAILED\|^E  " $O/r2_c11_tests.log | head -20
 timeout 900 python bench.py --steps 5 --warmup 3 > $O/r2_c11_bench.log 2>&1; tail -c 2500 $O/r2_c11_bench.log
