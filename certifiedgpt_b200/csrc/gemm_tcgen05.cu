@@ -889,15 +889,15 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
   // affords the same tiling everywhere with a TMA-store epilogue.  CGPT_GEMM_MT = 1 / 2 forces one form.
   const char* mt_env = getenv("CGPT_GEMM_MT");      // read per call: the tests switch it inside one process
   const int mt_forced = mt_env ? atoi(mt_env) : 0;
-  const bool big = ctas == 2 && bn == 256 && M >= 4096 && (mt_forced == 2 || (mt_forced == 0 && K >= 8192));
+  const bool big = ctas == 2 && bn == 256 && M >= 4096 && rp == nullptr && p.hm_T == 0 && p.red_inplace != 3 &&
+                   (mt_forced == 2 || (mt_forced == 0 && K >= 8192));   // common epilogues only
   if (big) p.group_m = p.group_m > 1 ? p.group_m / 2 : 1;
   // the 512-row tiles expose their epilogue: take the faster, sector-coalesced form of the in-place residual reductions
   // (llama_down sustained: 1217 -> 1267 TFLOP/s; with 256-row tiles the two forms tie, scripts/gemm_down_probe.py)
   if (big && p.red_inplace == 1 && p.ldo % 4 == 0 && !getenv("CGPT_GEMM_RED_DIRECT")) p.red_inplace = 2;
   if (rp != nullptr) {
     CGPT_REQUIRE(bn == 256, "gemm(rope): needs 256-wide N tiles (got %d)", bn);
-    rc = big ? launch_gemm<256, 2, MODE_ROPE, 2>(ta, tb, M, N, K, p, e->max_ctas, stream)
-       : ctas == 2 ? launch_gemm<256, 2, MODE_ROPE>(ta, tb, M, N, K, p, e->max_ctas, stream)
+    rc = ctas == 2 ? launch_gemm<256, 2, MODE_ROPE>(ta, tb, M, N, K, p, e->max_ctas, stream)
                    : launch_gemm<256, 1, MODE_ROPE>(ta, tb, M, N, K, p, e->max_ctas, stream);
   } else if (p.hm_T > 0) {
     rc = ctas == 2 ? launch_gemm<256, 2, MODE_HM>(ta, tb, M, N, K, p, e->max_ctas, stream)
