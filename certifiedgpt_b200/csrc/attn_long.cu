@@ -3,17 +3,16 @@
 //   (configs/eval_configs/vqav2_eval_noise_0.yaml:35; eva_vit.py:123-153).
 // Head-major q, k, v ([B][H][T][hd], see attn_vit.cu).  Work unit = (sample, head, PAIR of 128-query tiles); keys in tiles
 // of 128.  Softmax group g (4 warps, thread = query row) owns query tile 2 * pair + g with its own TMEM region
-// [S_g 128 columns | O_g hd columns]; BOTH groups consume every K / V tile from shared memory, so a tile is fetched from
-// L2 once per 256 query rows.  (The first version gave every 128-row unit its own pass over K and V: 32 GB of L2 -> SM
-// reads per layer at batch 256 = 6.1 TB/s, the chip's L2 bandwidth, and 5.3 ms - profiles/r02_ncu_kernels_summary.txt.)
-// All of S (1025 columns) does not fit TMEM, and reading it is the scarce resource: tcgen05.ld delivered ~77 bytes per
-// cycle per SM here, so a two-pass exact softmax (scores formed and read twice; the first version) spent its time
-// reading TMEM (profiles/r02_attn_long_probe.txt).  This version reads every score once: ONLINE softmax in 64-key steps
-// with the lazy rescale of FlashAttention-4: a row keeps a reference maximum m; a step whose maximum exceeds m by more
-// than 8 (log2 units) in some row of the warp multiplies that warp's rows of O (TMEM) and the running sums by
-// 2^(m - m_new) first; otherwise P = exp2(s - m) <= 2^8 is used as is - bf16 keeps its relative precision, the final
-// O / sum is the same quantity.  P replaces the scores in place (packed bf16) and is read by the tensor core as the A
-// operand of P.V; O accumulates in TMEM across the key tiles.
+// [S_g 128 columns | O_g 128 columns]; BOTH groups consume every K / V tile from shared memory, so a tile is fetched from
+// L2 once per 256 query rows (the first version gave every 128-row unit its own pass over K and V: 32 GB of L2 -> SM
+// reads per layer at batch 256; now 13.7 GB - profiles/r02_ncu_attention_final.txt).
+// All of S (1025 columns) does not fit TMEM.  The first version ran an exact two-pass softmax (scores formed and read
+// twice); this one forms and reads every score once: ONLINE softmax in 64-key steps with the lazy rescale of
+// FlashAttention-4: a row keeps a reference maximum m; a step whose maximum exceeds m by more than 8 (log2 units) in some
+// row of the warp multiplies that warp's rows of O (TMEM) and the running sums by 2^(m - m_new) first; otherwise
+// P = exp2(s - m) <= 2^8 is used as is - bf16 keeps its relative precision, the final O / sum is the same quantity.
+// P replaces the scores in place (packed bf16) and is read by the tensor core as the A operand of P.V; O accumulates in
+// TMEM across the key tiles.  History of the kernel, 5.29 -> 2.30 ms per layer: profiles/r02_attn_long_probe.txt.
 //   warp 0      TMA producer : the pair's two Q tiles, then K_0, V_0, K_1, V_1, ... through a 4-slot ring
 //   warps 1, 2  MMA issuers  : one thread per softmax group; per key tile P_h0.V, S_h0(next), P_h1.V, S_h1(next): while
 //               the group exponentiates one 64-key half, the tensor pipe consumes the other and refills it
