@@ -55,7 +55,7 @@ def main():
     tc = [k for k, c in per.items() if c["UTCMMA"]]
     legacy = [k for k, c in per.items() if c["HMMA"]]
     print(f"# kernels issuing tcgen05.mma: {len(tc)}; kernels on the legacy mma.sync path: {len(legacy)} "
-          f"(flash_attn_kernel / attention backward variants: Q-Former, 448 px ViT, tiny shapes, fine-tune backward)")
+          f"(flash_attn_kernel / attention backward variants: Q-Former, tiny shapes, the row-major ViT A/B path, fine-tune backward)")
 
 
 if __name__ == "__main__":
