@@ -41,7 +41,8 @@ constexpr int EPI_WARPS = 8;
 // TMEM accumulator stages belong to the same tile (no epilogue / mainloop overlap across tiles).  A third less L2 -> SM
 // traffic and fewer DRAM re-reads per FLOP; k-blocks of 64 so that four 48 KB stages fit.  This is cuBLAS's own tiling
 // for these shapes (nvjet 256x256 per CTA, 2cta; profiles/r02_gemm_vs_cublas.txt): the step runs at the 1 kW power cap,
-// where bytes moved per FLOP decide the throughput and an exposed epilogue only lets the clock rise.
+// where bytes moved per FLOP count; the exposed epilogue is paid for in time, so the tiling is used only where the
+// mainloop is long (K >= 8192, see the dispatch in gemm()).
 template <int BN, int CTAS, int MT = 1>
 struct GemmCfg {
   static constexpr int BK_ = MT == 2 ? 64 : BK;          // k-block of a pipeline stage
