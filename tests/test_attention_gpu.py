@@ -57,6 +57,36 @@ def test_non_causal_hd96_hd104_hd128(lib, force_flash):
     _run(lib, 3, 4, 256, 256, 128, False, force_flash)
 
 
+@pytest.mark.parametrize("B,H,hd,P,T_own,rows", [(6, 8, 128, 7, 76, 83),     # Llama decode: shared prefix + own rows, ragged tail of 3
+                                                   (3, 32, 128, 7, 73, 83),    # full head count, Tk = 80: exactly 10 iterations of 8
+                                                   (5, 4, 64, 0, 41, 41),      # no shared prefix, hd = 64
+                                                   (2, 4, 32, 3, 2, 9)])       # fewer keys than one iteration
+def test_single_token_decode_kernel(lib, B, H, hd, P, T_own, rows):
+    """decode_attn_kernel: one query row per sample against [shared prefix rows | the sample's own KV-cache rows]
+    (`rows` cache rows are allocated per sample, T_own of them valid)."""
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + H + hd)
+    D = H * hd
+    q = torch.randn(B, D, device="cuda", generator=g).bfloat16()
+    kc = torch.randn(B * rows, D, device="cuda", generator=g).bfloat16()
+    vc = torch.randn(B * rows, D, device="cuda", generator=g).bfloat16()
+    kp = torch.randn(max(P, 1), D, device="cuda", generator=g).bfloat16()
+    vp = torch.randn(max(P, 1), D, device="cuda", generator=g).bfloat16()
+    out = torch.full((B, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    scale = hd ** -0.5
+    lib.attention(q, kc, vc, out, B=B, H=H, Tq=1, Tk=P + T_own, head_dim=hd, scale=scale, q_rows_per_batch=1,
+                  kv_rows_per_batch=rows, kp=kp if P else None, vp=vp if P else None, P=P, decode=True)
+    torch.cuda.synchronize()
+    k_all = torch.cat([kp[:P].float().unsqueeze(0).expand(B, -1, -1), kc.float().view(B, rows, D)[:, :T_own]], 1)
+    v_all = torch.cat([vp[:P].float().unsqueeze(0).expand(B, -1, -1), vc.float().view(B, rows, D)[:, :T_own]], 1)
+    qh = q.float().view(B, H, 1, hd)
+    kh = k_all.view(B, -1, H, hd).transpose(1, 2)
+    vh = v_all.view(B, -1, H, hd).transpose(1, 2)
+    ref = ((qh @ kh.transpose(-1, -2) * scale).softmax(-1) @ vh).transpose(1, 2).reshape(B, D)
+    assert not torch.isnan(out.float()).any()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"max err {err}"
+
+
 def test_flash_only_shapes(lib):
     _run(lib, 3, 12, 32, 32, 64, False, False)          # Q-Former self
     _run(lib, 3, 12, 32, 257, 64, False, False)         # Q-Former cross
